@@ -1,0 +1,376 @@
+"""CPU ORACLE — TEST INFRASTRUCTURE ONLY.
+
+A functional, plain-torch (CPU, fp32) restatement of the reference's SignNet hot path.  Only `tests/`,
+`__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of `bench.py` may import this file; the
+product package `signnet_basisnet_b200` never does (its ops raise if the CUDA library is missing).
+
+Pinned: the reference ships no test or golden vector for this path, so the pin is against the
+reference's OWN modules run in the authoring container: `tests/test_oracle_vs_reference.py` runs every function here
+against the unmodified classes imported from /root/reference (oracle/ref_loader.py) on seeded inputs, and
+`oracle/make_golden.py` stores reference outputs/gradients as fixtures under tests/golden/ which both this oracle
+(`-m "not gpu"`) and the CUDA path (`-m gpu`) are checked against on the GPU box where /root/reference is absent.
+
+Every function takes the model's `state_dict` (reference key names) plus a key prefix, so the same
+tensors drive the reference module, this oracle and the CUDA modules.  Integer bookkeeping is numpy / int64 torch and
+must match bit-for-bit; floating point is fp32 with tolerance 1e-5 relative (BASELINE.json north_star).
+
+Third-party arithmetic restated here because its source is not under /root/reference:
+  torch_geometric 2.0.1 GINConv / GINEConv (pin: Alchemy/setup.sh:3-5), torch_scatter.scatter, dgl GINConv (unpinned).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# integer / layout bookkeeping (bit-exact rows a1, a2)
+# --------------------------------------------------------------------------------------------------------------------
+def graph_sizes(batch: torch.Tensor, num_graphs: int | None = None) -> np.ndarray:
+    """n_b per graph.  Follows `scatter(ones, batch)` sign_net.py:100 / transform.py:29."""
+    b = batch.numpy()
+    B = int(b.max()) + 1 if num_graphs is None else num_graphs
+    return np.bincount(b, minlength=B).astype(np.int64)
+
+
+def dense_list_evd(eig_vals: torch.Tensor, eig_vecs: torch.Tensor, batch: torch.Tensor):
+    """Ragged per-graph EVD -> dense-list layout.  Follows to_dense_EVD + to_dense_list_EVD
+    (Alchemy/sign_net/transform.py:26-49, :52-61) without the [B,Nmax,Nmax] detour:
+        eigS[i, j] = eigenvalue j of graph(i)         (j < n_b, else 0)
+        eigV[i, j] = V_b[local(i), j]                 (row-major flattened V, transform.py:14)
+    """
+    n = graph_sizes(batch)
+    nmax = int(n.max())
+    N = batch.numel()
+    node_ptr = np.concatenate([[0], np.cumsum(n)])
+    vec_ptr = np.concatenate([[0], np.cumsum(n * n)])
+    S = np.zeros((N, nmax), dtype=np.float32)
+    V = np.zeros((N, nmax), dtype=np.float32)
+    ev, evec = eig_vals.numpy(), eig_vecs.numpy()
+    for b in range(len(n)):
+        nb, p = int(n[b]), int(node_ptr[b])
+        S[p:p + nb, :nb] = ev[p:p + nb][None, :]
+        V[p:p + nb, :nb] = evec[vec_ptr[b]:vec_ptr[b] + nb * nb].reshape(nb, nb)
+    return torch.from_numpy(S), torch.from_numpy(V)
+
+
+def slot_mask(batch: torch.Tensor, k: int) -> torch.Tensor:
+    """mask_full[i, j] = j < n_{batch[i]}  (sign_net.py:100-102; DGL twin deepsigns.py:66-78)."""
+    n = torch.from_numpy(graph_sizes(batch))
+    return torch.arange(k)[None, :] < n[batch][:, None]
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# shared pieces
+# --------------------------------------------------------------------------------------------------------------------
+def _bn(x2d, sd, p, training):
+    """nn.BatchNorm1d on [M, C] rows: batch stats (biased var) + running update (unbiased, momentum .1) in training,
+    running stats in eval.  Buffers in `sd` are updated in place like the module would."""
+    rm, rv = sd.get(p + "running_mean"), sd.get(p + "running_var")
+    use_batch = training or rm is None
+    y = F.batch_norm(x2d, None if rm is None else rm, None if rv is None else rv, sd[p + "weight"], sd[p + "bias"],
+                     use_batch, BN_MOMENTUM, BN_EPS)
+    if training and (p + "num_batches_tracked") in sd:
+        sd[p + "num_batches_tracked"] += 1
+    return y
+
+
+def gin_aggregate(x, edge_index, eps):
+    """K1.  PyG 2.0.1 GINConv core on node dim -2:  out = scatter_add(x[src] -> dst) ; out += (1+eps)*x
+    (masked_layers.py:70,75).  Order of the fp32 adds: edges in edge-id order from zero, then the self term."""
+    out = torch.zeros_like(x).index_add_(-2, edge_index[1], x.index_select(-2, edge_index[0]))
+    return out + (1 + eps) * x
+
+
+def _masked_bn(x, mask, sd, p, training):
+    """MaskedBN (masked_layers.py:13-20): BN over the valid rows only, other rows untouched."""
+    if mask is None:
+        sh = x.shape
+        return _bn(x.reshape(-1, sh[-1]), sd, p + "bn.", training).reshape(sh)
+    out = x.clone()
+    out[mask] = _bn(x[mask], sd, p + "bn.", training)
+    return out
+
+
+def masked_mlp(x, mask, sd, p, nlayer=2, with_final_activation=True, training=True):
+    """MaskedMLP.forward (masked_layers.py:54-64).  The last norm exists in the state_dict but is skipped when
+    with_final_activation=False (:61)."""
+    for i in range(nlayer):
+        x = F.linear(x, sd[f"{p}layers.{i}.weight"], sd.get(f"{p}layers.{i}.bias"))
+        if mask is not None:
+            x = x * mask.unsqueeze(-1)
+        if i < nlayer - 1 or with_final_activation:
+            x = F.relu(_masked_bn(x, mask, sd, f"{p}norms.{i}.", training))
+    return x
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# PyG flavour: phi = GNN3d of MaskedGINConv (rows a3-a7)
+# --------------------------------------------------------------------------------------------------------------------
+def gnn3d(x, edge_index, mask, sd, p, n_layer, training=True):
+    """GNN3d.forward (Alchemy/sign_net/sign_net.py:28-44) on x [N,k,d_in], mask [N,k] -> [N,k,d].
+    Per layer: MaskedGINConv (aggregate -> MaskedMLP(2 layers, no final act)) -> zero masked ->
+    MaskedBN -> ReLU -> + previous."""
+    x = x.transpose(0, 1)
+    m = None if mask is None else mask.transpose(0, 1)
+    prev = 0
+    for l in range(n_layer):
+        a = gin_aggregate(x, edge_index, sd[f"{p}convs.{l}.layer.eps"])
+        y = masked_mlp(a, m, sd, f"{p}convs.{l}.nn.", 2, False, training)
+        if m is not None:
+            y = y * m.unsqueeze(-1)
+        y = F.relu(_masked_bn(y, m, sd, f"{p}norms.{l}.", training))
+        x = y + prev
+        prev = x
+    return x.transpose(0, 1)
+
+
+def phi_pm(eigV, edge_index, mask, sd, p, n_layer, training=True):
+    """phi(+v) + phi(-v) (sign_net.py:113): two separate passes => per-sign BN batch statistics and two running-stat
+    updates per step, +v first."""
+    x = eigV.unsqueeze(-1)
+    return gnn3d(x, edge_index, mask, sd, p, n_layer, training) + gnn3d(-x, edge_index, mask, sd, p, n_layer, training)
+
+
+def _masked_ln(x, mask, sd, p):
+    out = x.clone()
+    out[mask] = F.layer_norm(x[mask], (x.shape[-1],), sd[p + "ln.weight"], sd[p + "ln.bias"], 1e-6)
+    return out
+
+
+def set_transformer(x, pos, mask, sd, p, n_layer, n_head=4, training=True, attn_dropout=0.0):
+    """rho of the PyG trees: SetTransformer.forward (sign_net.py:60-72) with TransformerEncoderLayer
+    (transformer_module.py:34-42), MultiHeadAttention (:76-102, post-LN eps 1e-6), masked softmax with -1e10 fill
+    (:51-58) and FFN (:113-127).  x [N,k,d], pos [N,k,d] or 0, mask [N,k].
+    Reference quirk: MultiHeadAttention builds ScaledDotProductAttention with its default attn_dropout=0.1
+    (transformer_module.py:46,85), so in training mode the reference rho is stochastic; parity is checked with that
+    dropout at 0 (training) and in eval mode.  `attn_dropout` restates it for the timed CPU baseline."""
+    x = x + pos
+    N, k, d = x.shape
+    dk = d // n_head
+    mk = mask.unsqueeze(-1)
+    pair = (mask.unsqueeze(1) * mask.unsqueeze(2)).unsqueeze(1)  # [N,1,k,k]
+    for l in range(n_layer):
+        q = f"{p}transformer_layers.{l}."
+        res = x
+        Q = F.linear(x, sd[q + "slf_attn.w_qs.weight"]).view(N, k, n_head, dk).transpose(1, 2)
+        K = F.linear(x, sd[q + "slf_attn.w_ks.weight"]).view(N, k, n_head, dk).transpose(1, 2)
+        V = F.linear(x, sd[q + "slf_attn.w_vs.weight"]).view(N, k, n_head, dk).transpose(1, 2)
+        att = torch.matmul(Q / dk ** 0.5, K.transpose(2, 3)).masked_fill(pair == 0, -1e10)
+        att = F.softmax(att, dim=-1)
+        if training and attn_dropout > 0:
+            att = F.dropout(att, attn_dropout, True)
+        att = att * pair
+        o = torch.matmul(att, V).transpose(1, 2).contiguous().view(N, k, -1)
+        o = F.linear(o, sd[q + "slf_attn.fc.weight"]) + res
+        x = _masked_ln(o, mask, sd, q + "slf_attn.norm.") * mk
+        res = x
+        h = F.relu(F.linear(x, sd[q + "pos_ffn.w_1.weight"], sd[q + "pos_ffn.w_1.bias"])) * mk
+        h = F.linear(h, sd[q + "pos_ffn.w_2.weight"], sd[q + "pos_ffn.w_2.bias"]) * mk
+        x = _masked_ln(h + res, mask, sd, q + "pos_ffn.norm.") * mk
+    x = x.sum(dim=1)
+    x = F.linear(x, sd[p + "out.0.weight"])
+    return _bn(x, sd, p + "out.1.", training)
+
+
+def sign_net(eigS, eigV, edge_index, batch, sd, p, nl_phi, nl_rho, ignore_eigval=False, training=True,
+             attn_dropout=0.0):
+    """SignNet.forward (sign_net.py:96-118) from the dense-list tensors: [N,k] -> [N,n_hid]."""
+    mask = slot_mask(batch, eigV.shape[1])
+    pos = 0
+    if not ignore_eigval:
+        pos = masked_mlp(eigS.unsqueeze(-1), mask, sd, p + "eigen_encoder.", 2, True, training)
+    x = phi_pm(eigV, edge_index, mask, sd, p + "phi.", nl_phi, training)
+    return set_transformer(x, pos, mask, sd, p + "rho.", nl_rho, 4, training, attn_dropout)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# PyG flavour: downstream GNN predictor with GINEConv (row a12)
+# --------------------------------------------------------------------------------------------------------------------
+def _mlp(x, sd, p, nlayer, with_final_activation=True, with_norm=True, training=True):
+    """elements.MLP.forward (elements.py:39-69)."""
+    for i in range(nlayer):
+        x = F.linear(x, sd[f"{p}layers.{i}.weight"], sd.get(f"{p}layers.{i}.bias"))
+        if i < nlayer - 1 or with_final_activation:
+            if with_norm:
+                x = _bn(x, sd, f"{p}norms.{i}.", training)
+            x = F.relu(x)
+    return x
+
+
+def _discrete_encoder(x, sd, p):
+    """DiscreteEncoder.forward (elements.py:31-37): sum of per-column embeddings."""
+    if x.dim() == 1:
+        x = x.unsqueeze(1)
+    out = 0
+    for i in range(x.size(1)):
+        out = out + F.embedding(x[:, i], sd[f"{p}embeddings.{i}.weight"])
+    return out
+
+
+def gine_aggregate(x, edge_index, edge_emb, eps):
+    """K6.  PyG GINEConv core: sum_j relu(x_j + e_ij) into i, then += (1+eps) x_i (pyg_gnn_wrapper.py:23,28)."""
+    msg = (x.index_select(0, edge_index[0]) + edge_emb).relu()
+    out = torch.zeros_like(x).index_add_(0, edge_index[1], msg)
+    return out + (1 + eps) * x
+
+
+def gnn_predictor(x_in, edge_index, edge_attr, batch, pos, sd, p, nlayer, num_graphs=None, training=True):
+    """GNN.forward (Alchemy/sign_net/model.py:36-64), gnn_type='GINEConv', pooling='add', bn, res.
+    Discrete (ZINC) vs continuous (Alchemy) inputs are told apart by the state_dict keys, as in model.py:13-14."""
+    if f"{p}input_encoder.embeddings.0.weight" in sd:
+        x = _discrete_encoder(x_in.squeeze(), sd, p + "input_encoder.")
+    else:
+        x = _mlp(x_in.squeeze(), sd, p + "input_encoder.", 1, training=training)
+    if pos is not None:
+        x = F.linear(torch.cat([x, pos], dim=-1), sd[p + "linear.weight"], sd[p + "linear.bias"])
+    if edge_attr is None:
+        edge_attr = edge_index.new_zeros(edge_index.size(-1))
+    prev = x
+    for l in range(nlayer):
+        if f"{p}edge_encoders.{l}.embeddings.0.weight" in sd:
+            e = _discrete_encoder(edge_attr, sd, f"{p}edge_encoders.{l}.")
+        else:
+            e = _mlp(edge_attr, sd, f"{p}edge_encoders.{l}.", 1, training=training)
+        a = gine_aggregate(x, edge_index, e, sd[f"{p}convs.{l}.layer.eps"])
+        x = _mlp(a, sd, f"{p}convs.{l}.nn.", 2, False, True, training)
+        x = F.relu(_bn(x, sd, f"{p}norms.{l}.", training))
+        x = x + prev
+        prev = x
+    B = int(batch.max()) + 1 if num_graphs is None else num_graphs
+    x = torch.zeros(B, x.shape[1]).index_add_(0, batch, x)  # K5 add-pool (model.py:61)
+    return _mlp(x, sd, p + "output_encoder.", 2, False, True, training)
+
+
+def sign_net_gnn(data, sd, nl_signnet, nl_gnn, nl_rho=4, ignore_eigval=False, training=True, attn_dropout=0.0):
+    """SignNetGNN.forward (sign_net.py:130-132)."""
+    eigS, eigV = dense_list_evd(data.eigen_values, data.eigen_vectors, data.batch)
+    pos = sign_net(eigS, eigV, data.edge_index, data.batch, sd, "sign_net.", nl_signnet, nl_rho, ignore_eigval, training,
+                   attn_dropout)
+    return gnn_predictor(data.x, data.edge_index, data.edge_attr, data.batch, pos, sd, "gnn.", nl_gnn, training=training)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# DGL flavour (rows a9-a11): GIN phi on [N,k,C] with unmasked BN, rho = MLP
+# --------------------------------------------------------------------------------------------------------------------
+def _bn_nkc(x, sd, p, training):
+    """BatchNorm1d applied as bn(x.transpose(2,1)).transpose(2,1) on [N,k,C] == BN over all N*k rows (padded slots
+    included), gnns.py:107-112 / mlp.py:42-46."""
+    if x.ndim == 2:
+        return _bn(x, sd, p, training)
+    sh = x.shape
+    return _bn(x.reshape(-1, sh[-1]), sd, p, training).reshape(sh)
+
+
+def dgl_mlp(x, sd, p, num_layers, training=True):
+    """layers/mlp.py:37-56 with use_bn=True, relu, dropout 0: (Linear -> ReLU -> BN) x (L-1) -> Linear."""
+    for i in range(num_layers - 1):
+        x = F.relu(F.linear(x, sd[f"{p}lins.{i}.weight"], sd[f"{p}lins.{i}.bias"]))
+        x = _bn_nkc(x, sd, f"{p}bns.{i}.", training)
+    i = num_layers - 1
+    return F.linear(x, sd[f"{p}lins.{i}.weight"], sd[f"{p}lins.{i}.bias"])
+
+
+def dgl_gin(x, src, dst, sd, p, n_layers, training=True):
+    """GIN.forward (layers/gnns.py:102-114): layer i>0 is preceded by BN_{i-1}; dgl GINConv('sum', eps buffer 0):
+    rst = (1+eps)*feat + sum_{u->v} feat_u ; apply_func = 2-layer MLP."""
+    for i in range(n_layers):
+        if i != 0:
+            x = _bn_nkc(x, sd, f"{p}bns.{i - 1}.", training)
+        eps = sd.get(f"{p}layers.{i}.eps", torch.zeros(1))
+        neigh = torch.zeros_like(x).index_add_(0, dst, x.index_select(0, src))
+        x = dgl_mlp((1 + eps) * x + neigh, sd, f"{p}layers.{i}.apply_func.", 2, training)
+    return x
+
+
+def gin_deepsigns(x, src, dst, sd, n_layers, k, training=True):
+    """GINDeepSigns.forward (layers/deepsigns.py:45-51): x [N,k,1] -> [N,k,1]."""
+    h = dgl_gin(x, src, dst, sd, "enc.", n_layers, training) + dgl_gin(-x, src, dst, sd, "enc.", n_layers, training)
+    h = dgl_mlp(h.reshape(h.shape[0], -1), sd, "rho.", n_layers, training)
+    return h.reshape(x.shape[0], k, 1)
+
+
+def masked_gin_deepsigns(x, src, dst, num_nodes_per_graph, sd, n_layers, k, training=True):
+    """MaskedGINDeepSigns.forward (layers/deepsigns.py:72-86): zero slots >= n_b, sum over k, rho MLP."""
+    h = dgl_gin(x, src, dst, sd, "enc.", n_layers, training) + dgl_gin(-x, src, dst, sd, "enc.", n_layers, training)
+    n_per_node = torch.repeat_interleave(num_nodes_per_graph, num_nodes_per_graph)
+    mask = torch.arange(x.shape[1])[None, :] < n_per_node[:, None]
+    h = (h * mask.unsqueeze(-1)).sum(dim=1)
+    h = dgl_mlp(h, sd, "rho.", n_layers, training)
+    return h.reshape(x.shape[0], k, 1)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# LearningFilters flavour (rows a14, a15): single-graph SignNet (DeepSets phi) and BasisNet IGN 2->1
+# --------------------------------------------------------------------------------------------------------------------
+def eq_deepsets(x, sd, p, num_layers, use_bn=True):
+    """EqDeepSetsEncoder.forward (LearningFilters/models.py:91-113): per-element Linear + Linear(mean over the set
+    dim -2); ReLU; BN(track_running_stats=False => always batch stats)."""
+    for i in range(num_layers - 1):
+        x = F.relu(F.linear(x, sd[f"{p}lins1.{i}.weight"], sd[f"{p}lins1.{i}.bias"])
+                   + F.linear(x.mean(dim=-2, keepdim=True), sd[f"{p}lins2.{i}.weight"], sd[f"{p}lins2.{i}.bias"]))
+        if use_bn:
+            sh = x.shape
+            x = F.batch_norm(x.reshape(-1, sh[-1]), None, None, sd[f"{p}bns.{i}.weight"], sd[f"{p}bns.{i}.bias"],
+                             True, BN_MOMENTUM, BN_EPS).reshape(sh)
+    i = num_layers - 1
+    return (F.linear(x, sd[f"{p}lins1.{i}.weight"], sd[f"{p}lins1.{i}.bias"])
+            + F.linear(x.mean(dim=-2, keepdim=True), sd[f"{p}lins2.{i}.weight"], sd[f"{p}lins2.{i}.bias"]))
+
+
+def sign_plus_deepsets(x, sd, p, num_layers, use_bn=True):
+    """SignPlus.forward (LearningFilters/signbasisnet.py:16-20): model(x) + model(-x)."""
+    return eq_deepsets(x, sd, p, num_layers, use_bn) + eq_deepsets(-x, sd, p, num_layers, use_bn)
+
+
+def ign_2to1_ops(P):
+    """contractions_2_to_1 (LearningFilters/ign.py:344-374) on P [b, d, m, m] -> [b, d, 5, m]:
+    diag, trace/m, rowsum/m, colsum/m, total/m^2 (normalised)."""
+    m = P.shape[-1]
+    diag = torch.diagonal(P, dim1=-2, dim2=-1)
+    tr = diag.sum(-1, keepdim=True)
+    row = P.sum(dim=3)
+    col = P.sum(dim=2)
+    tot = row.sum(-1, keepdim=True)
+    return torch.stack([diag, tr.expand_as(diag) / m, row / m, col / m, tot.expand_as(diag) / m ** 2], dim=2)
+
+
+def ign_1to1_ops(x):
+    """contractions_1_to_1 (ign.py:404-417): identity and mean over the set."""
+    return torch.stack([x, x.sum(dim=2, keepdim=True).expand_as(x) / x.shape[2]], dim=2)
+
+
+def ign2to1(P, sd, p="", training=True):
+    """IGN2to1.forward (LearningFilters/ign.py:29-39): 2->1 equivariant layer, two 1->1 layers (each: einsum with
+    coeffs [D,S,basis] + bias, ReLU, then BN over channel dim of [b,S,m]), then fc1/ReLU/fc2 on the channel dim.
+    P [b,1,m,m] -> [b,out,m]."""
+    def bn3(x, q):
+        y = F.batch_norm(x, sd[q + "running_mean"], sd[q + "running_var"], sd[q + "weight"], sd[q + "bias"],
+                         training, BN_MOMENTUM, BN_EPS)
+        if training and (q + "num_batches_tracked") in sd:
+            sd[q + "num_batches_tracked"] += 1
+        return y
+
+    ops = [ign_2to1_ops, ign_1to1_ops, ign_1to1_ops]
+    x = P
+    for i in range(3):
+        x = torch.einsum("dsb,ndbi->nsi", sd[f"{p}equi_layers.{i}.coeffs"], ops[i](x)) + sd[f"{p}equi_layers.{i}.bias"]
+        x = bn3(F.relu(x), f"{p}bns.{i}.")
+    x = x.transpose(2, 1)
+    x = F.relu(F.linear(x, sd[p + "fc1.weight"], sd[p + "fc1.bias"]))
+    x = F.linear(x, sd[p + "fc2.weight"], sd[p + "fc2.bias"])
+    return x.transpose(2, 1)
+
+
+def eigenspace_groups(eigvals: torch.Tensor, decimals: int = 5):
+    """Eigenvalue grouping of LearningFilters/training.py:47-62: round to `decimals`, unique -> (counts, sections).
+    Returns a list of (start, stop) column ranges, one per eigenspace, in ascending eigenvalue order."""
+    r = torch.round(eigvals * 10 ** decimals) / (10 ** decimals)
+    _, counts = r.unique(return_counts=True)
+    stops = torch.cumsum(counts, 0).tolist()
+    starts = [0] + stops[:-1]
+    return list(zip(starts, stops))

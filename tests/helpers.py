@@ -1,0 +1,27 @@
+"""Shared comparison helpers for the parity tests."""
+import torch
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor, floor: float = 0.0) -> float:
+    """max|a-b| / max(max|b|, floor): the '1e-5 relative fp32' measure of BASELINE.json's north_star, taken per
+    tensor (element-wise relative error is meaningless where the reference value is rounding noise around 0)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    denom = max(float(b.abs().max()) if b.numel() else 0.0, floor, 1e-30)
+    return float((a - b).abs().max()) / denom if a.numel() else 0.0
+
+
+def assert_close_rel(a, b, tol, floor=0.0, what=""):
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    e = rel_err(a, b, floor)
+    assert e <= tol, f"{what}: relative error {e:.3e} > {tol:.1e}"
+
+
+def assert_grads_close(named_got, named_ref, tol, what=""):
+    """Gradients of all parameters; parameters whose true gradient is ~0 (e.g. a bias feeding BatchNorm) are compared
+    against the scale of the largest gradient in the model (x0.1: their noise is the rounding error of O(gmax) cancelling terms) instead of their own rounding noise."""
+    ref = {k: v for k, v in named_ref.items() if v is not None}
+    gmax = max((float(v.abs().max()) for v in ref.values()), default=0.0)
+    for k, v in ref.items():
+        g = named_got.get(k)
+        assert g is not None, f"{what}: no gradient for {k}"
+        assert_close_rel(g, v, tol, floor=0.1 * gmax, what=f"{what} grad {k}")

@@ -1,0 +1,142 @@
+/* libsignnet_b200 — C ABI of the B200-native SignNet hot path.
+ *
+ * The reference (cptq/SignNet-BasisNet) has no FFI: its boundary for this path is the nn.Module surface
+ * (Alchemy/sign_net/sign_net.py:74-132, GraphPrediction/layers/deepsigns.py:33-86) and, beneath it, calls into
+ * third-party graph libraries.  Each entry point below replaces one of those library call sites (cited per function);
+ * the Python modules in signnet_basisnet_b200/ bind them with ctypes exactly as INTEGRATION.md shows.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch caching allocator); nothing is allocated, retained
+ *     or freed here; `stream` is a cudaStream_t (torch.cuda.current_stream().cuda_stream), all work is enqueued on it;
+ *   - return value 0 = ok, non-zero = error, message via sb_last_error() (thread-local);
+ *   - index data at the API is int64 (`edge_index`, `batch`) as in PyG/DGL; floating point is fp32;
+ *   - "slot rows": activations of phi live in the ragged layout  row(b, j, i) = row_ptr[b] + j*n_b + i
+ *     (graph b, eigenvector slot j < k_b, local node i < n_b), as a [S, R, ld] tensor (S = 2 sign passes,
+ *     ld = feature dim rounded up to 4 floats, padding columns kept at 0).  Only valid slots exist, so the reference's
+ *     boolean-mask bookkeeping (sign_net.py:38-39, masked_layers.py:59-60) has no counterpart.
+ *   - `G` ("groups") = leading dimension over which BatchNorm statistics are kept separate (the two sign passes).
+ */
+#ifndef SIGNNET_B200_H
+#define SIGNNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_ABI_VERSION 1
+
+/* bits of the `flags` word written by the bookkeeping kernels (device int32, caller zero-initialises) */
+#define SB_FLAG_BATCH_UNSORTED 1   /* `batch` is not non-decreasing */
+#define SB_FLAG_BATCH_RANGE 2      /* `batch` value outside [0, B) */
+#define SB_FLAG_EDGE_RANGE 4       /* edge endpoint outside [0, N) */
+#define SB_FLAG_EDGE_CROSS_GRAPH 8 /* an edge joins two different graphs of the batch */
+
+const char* sb_last_error(void);
+int sb_abi_version(void);
+int sb_device_sm_count(void);
+
+/* ---- bookkeeping (bit-exact integer work) ------------------------------------------------------------------------ */
+
+/* graph_ptr[B+1] (int32 node offsets) from the sorted batch vector.
+ * Replaces scatter(ones, batch) + cumsum: Alchemy/sign_net/transform.py:28-30, sign_net.py:100. */
+int sb_graph_ptr(const int64_t* batch, int64_t N, int32_t B, int32_t* graph_ptr, int32_t* flags, void* stream);
+
+/* Slot-row layout. k_b = masked ? min(n_b,k) : k.  row_ptr[B+1] = prefix(n_b*k_b); vec_ptr[B+1] = prefix(n_b^2)
+ * (offsets into the ragged eigen_vectors, transform.py:14); unit_ptr[B+1] = prefix of aggregate work units for
+ * `tile_rows`; summary[6] = {R, n_max, max k_b, sum n_b^2, #units, #graphs with n_b > tile_rows}.
+ * Replaces the mask construction sign_net.py:100-102 / deepsigns.py:66-78 and to_dense_EVD's index math. */
+int sb_slot_layout(const int32_t* graph_ptr, int32_t B, int32_t k, int32_t masked, int32_t tile_rows,
+                   int64_t* row_ptr, int64_t* vec_ptr, int32_t* unit_ptr, int64_t* summary, void* stream);
+int sb_agg_units(const int32_t* graph_ptr, int32_t B, int32_t k, int32_t masked, int32_t tile_rows,
+                 int32_t* unit_ptr, void* stream);
+
+/* Stable CSR by destination (in_*) and by source (out_*) of edge_index[2,E]; rows keep edge-id order so neighbour
+ * sums accumulate in the order torch's CPU index_add_ uses.  workspace: >= 2*(N+1) + 2*ceil((N+1)/4096) int32.
+ * Replaces the per-call gather/scatter indexing inside PyG MessagePassing.propagate / DGL update_all. */
+int sb_build_csr(const int64_t* edge_index, int64_t E, int64_t N, const int64_t* batch, int32_t* in_ptr,
+                 int32_t* in_src, int32_t* in_eid, int32_t* out_ptr, int32_t* out_dst, int32_t* out_eid,
+                 int32_t* workspace, int64_t workspace_ints, int32_t* flags, void* stream);
+
+/* phi input x0[2, R]: +/- eigenvector entries in slot-row order, from the ragged per-graph V (row-major [node, eig])
+ * or from a dense-list tensor eigvecs[N, >=k].  Replaces to_dense_list_EVD + unsqueeze/transpose + `-x`
+ * (transform.py:52-61, sign_net.py:104,113; GNN3d :31). */
+int sb_phi_input_ragged(const float* eigen_vectors, const int64_t* batch, const int32_t* graph_ptr,
+                        const int64_t* row_ptr, const int64_t* vec_ptr, int64_t N, int32_t k, int32_t masked,
+                        int64_t R, float* x0, void* stream);
+int sb_phi_input_dense(const float* eigvecs, int64_t ld, const int64_t* batch, const int32_t* graph_ptr,
+                       const int64_t* row_ptr, int64_t N, int32_t k, int32_t masked, int64_t R, float* x0,
+                       void* stream);
+/* eigenvalue feature per slot row (input of SignNet.eigen_encoder, sign_net.py:107-108) */
+int sb_slot_eigval(const float* eigen_values, const int64_t* batch, const int32_t* graph_ptr, const int64_t* row_ptr,
+                   int64_t N, int32_t k, int32_t masked, float* out, void* stream);
+/* to_dense_list_EVD itself (transform.py:52-61): eigS/eigV [N, nmax] zero padded, mask[N, nmax] (any may be NULL) */
+int sb_dense_list_evd(const float* eigen_values, const float* eigen_vectors, const int64_t* batch,
+                      const int32_t* graph_ptr, const int64_t* vec_ptr, int64_t N, int32_t nmax, float* eigS,
+                      float* eigV, uint8_t* mask, void* stream);
+
+/* slot rows <-> the reference's padded dense view [N, k, C] (return value of GNN3d, sign_net.py:44; phi(x)+phi(-x),
+ * sign_net.py:113 / deepsigns.py:73).  rows_to_dense sums over the S sign passes; dense_to_rows writes +v (and -v or a
+ * copy) and zero-fills the padding columns. */
+int sb_rows_to_dense(const float* rows, int64_t ld, int64_t R, int32_t S, const int64_t* batch,
+                     const int32_t* graph_ptr, const int64_t* row_ptr, int64_t N, int32_t k, int32_t masked,
+                     int32_t C, float* dense, void* stream);
+int sb_dense_to_rows(const float* dense, int64_t R, int32_t S, int32_t negate_second, const int64_t* batch,
+                     const int32_t* graph_ptr, const int64_t* row_ptr, int64_t N, int32_t k, int32_t masked,
+                     int32_t C, int64_t ld, float* rows, void* stream);
+
+/* ---- K1: GIN neighbourhood aggregate ------------------------------------------------------------------------------
+ * out = [res +] (1+eps)*x + sum_{nbr} x   on [S, R, ld] slot rows; (nbr_ptr, nbr_idx) = CSR by destination for the
+ * forward, by source for the backward.  Optional dot_out += sum(x * dotx) (= d eps in the backward).
+ * Replaces gnn.GINConv(Identity(), train_eps=True) (masked_layers.py:70,75) / dgl GINConv(.,'sum') (gnns.py:90-98). */
+int sb_gin_agg(const float* x, float* out, const float* res, const float* dotx, double* dot_out, const float* eps,
+               const int32_t* graph_ptr, const int32_t* unit_ptr, const int64_t* row_ptr, const int32_t* nbr_ptr,
+               const int32_t* nbr_idx, int64_t R, int32_t B, int32_t k, int32_t masked, int32_t S, int32_t ld,
+               int32_t tile_rows, int32_t force_generic, void* stream);
+int sb_gin_agg_tile_rows(int32_t ld); /* rows per shared-memory tile of the TMA path (0 = generic path only) */
+
+/* ---- K2: Linear with fused BatchNorm prologue / statistics epilogue ------------------------------------------------
+ * y[g*R+r, n] (+)= sum_k f(x[g*R+r, k]) * W[n*w_rs + k*w_cs] + bias[n];  f: pro 0 none, 1 pa*x+pc, 2 relu(pa*x+pc)
+ * with pa/pc [G, K]; optional relu on the output; stats[G,2,N] += column sum / sum of squares of the output (fp64).
+ * Columns N..ldy-1 of y are zero-filled.  Replaces nn.Linear + mask writes in MaskedMLP (masked_layers.py:54-64),
+ * layers/mlp.py:37-56, elements.py:57-65. */
+int sb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t w_rs, int64_t w_cs, const float* bias,
+                  float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N, int32_t pro, const float* pa,
+                  const float* pc, int32_t relu, double* stats, int32_t accumulate, void* stream);
+/* dw[n*rs + k*cs] (+)= sum gy[., n] * f(x[., k]);  db[n] (+)= sum gy[., n]   (deterministic two-stage reduction) */
+int sb_linear_wgrad(const float* gy, int64_t ldg, const float* x, int64_t ldx, int64_t R, int32_t G, int32_t N,
+                    int32_t K, int32_t pro, const float* pa, const float* pc, float* dw, int64_t dw_rs,
+                    int64_t dw_cs, float* db, int32_t accumulate, float* workspace, void* stream);
+int64_t sb_linear_wgrad_workspace_floats(void);
+
+/* ---- K3/K4: BatchNorm over slot rows + element-wise glue -----------------------------------------------------------
+ * Replaces MaskedBN (masked_layers.py:13-20) / nn.BatchNorm1d (gnns.py:107-112, mlp.py:42-46). */
+int sb_col_stats(const float* x, int64_t ld, int64_t R, int32_t G, int32_t C, double* stats, void* stream);
+int sb_bn_finalize(const double* stats, int64_t M, int32_t G, int32_t C, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, float momentum, float eps, int32_t training, float* a,
+                   float* c, float* mean, float* rstd, void* stream);
+/* out = act(pa*y + pc) + res  (GNN3d tail: norm -> relu -> residual, sign_net.py:40-43) */
+int sb_affine_act_res(const float* y, const float* pa, const float* pc, const float* res, float* out, int64_t ld,
+                      int64_t R, int32_t G, int32_t C, int32_t relu, void* stream);
+int sb_bn_bwd_reduce(const float* gout, const float* y, const float* pa, const float* pc, const float* mean,
+                     const float* rstd, float* dz, int64_t ld, int64_t R, int32_t G, int32_t C, int32_t relu,
+                     double* stats, void* stream);
+int sb_bn_bwd_finalize(const double* stats, int64_t M, int32_t G, int32_t C, const float* pa, const float* mean,
+                       const float* rstd, int32_t training, int32_t accumulate, float* dgamma, float* dbeta,
+                       float* al, float* be, float* ga, void* stream);
+int sb_affine2(const float* t1, const float* t2, const float* al, const float* be, const float* ga, float* out,
+               int64_t ld, int64_t R, int32_t G, int32_t C, void* stream);
+
+/* sum over eigenvector slots and sign passes -> [N, ldo]  (sign_net.py:113 + :70 ; deepsigns.py:72-81) */
+int sb_slot_sum_fwd(const float* x, int64_t ld, int64_t R, int32_t S, const int64_t* batch, const int32_t* graph_ptr,
+                    const int64_t* row_ptr, int64_t N, int32_t k, int32_t masked, int32_t limit_by_n, float* out,
+                    int64_t ldo, int32_t C, void* stream);
+int sb_slot_sum_bwd(const float* gout, int64_t ldo, float* gx, int64_t ld, int64_t R, int32_t S,
+                    const int64_t* batch, const int32_t* graph_ptr, const int64_t* row_ptr, int64_t N, int32_t k,
+                    int32_t masked, int32_t limit_by_n, int32_t C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGNNET_B200_H */

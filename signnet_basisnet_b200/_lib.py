@@ -1,0 +1,129 @@
+"""ctypes binding of libsignnet_b200.so (the C ABI declared in include/signnet_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsignnet_b200.so")
+
+# p = device pointer (or NULL), l = int64, i = int32, f = float
+_SIGNATURES = {
+    "sb_graph_ptr": "plipp" + "p",
+    "sb_slot_layout": "piiii" + "pppp" + "p",
+    "sb_agg_units": "piiii" + "p" + "p",
+    "sb_build_csr": "pllp" + "pppppp" + "plp" + "p",
+    "sb_phi_input_ragged": "ppppp" + "liil" + "p" + "p",
+    "sb_phi_input_dense": "plppp" + "liil" + "p" + "p",
+    "sb_slot_eigval": "pppp" + "lii" + "p" + "p",
+    "sb_dense_list_evd": "ppppp" + "li" + "ppp" + "p",
+    "sb_rows_to_dense": "pll" + "i" + "ppp" + "l" + "iii" + "p" + "p",
+    "sb_dense_to_rows": "pl" + "ii" + "ppp" + "l" + "iii" + "l" + "p" + "p",
+    "sb_gin_agg": "ppppp" + "p" + "ppppp" + "l" + "iiiiiii" + "p",
+    "sb_linear_fwd": "pl" + "pll" + "p" + "pl" + "l" + "iii" + "ipp" + "i" + "p" + "i" + "p",
+    "sb_linear_wgrad": "pl" + "pl" + "l" + "iii" + "ipp" + "pll" + "p" + "i" + "p" + "p",
+    "sb_col_stats": "pll" + "ii" + "p" + "p",
+    "sb_bn_finalize": "pl" + "ii" + "pppp" + "ff" + "i" + "pppp" + "p",
+    "sb_affine_act_res": "ppppp" + "ll" + "iii" + "p",
+    "sb_bn_bwd_reduce": "ppppppp" + "ll" + "iii" + "p" + "p",
+    "sb_bn_bwd_finalize": "pl" + "ii" + "ppp" + "ii" + "ppppp" + "p",
+    "sb_affine2": "pppppp" + "ll" + "ii" + "p",
+    "sb_slot_sum_fwd": "pll" + "i" + "ppp" + "l" + "iii" + "pl" + "i" + "p",
+    "sb_slot_sum_bwd": "pl" + "pll" + "i" + "ppp" + "l" + "iii" + "i" + "p",
+}
+_CT = {"p": ctypes.c_void_p, "l": ctypes.c_int64, "i": ctypes.c_int32, "f": ctypes.c_float}
+
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LibraryMissing(
+                f"{LIB_PATH} not found: build it with `python -m signnet_basisnet_b200.build` "
+                "(there is no CPU or PyTorch fallback for the SignNet hot path)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.sb_last_error.restype = ctypes.c_char_p
+        L.sb_abi_version.restype = ctypes.c_int
+        L.sb_device_sm_count.restype = ctypes.c_int
+        L.sb_gin_agg_tile_rows.restype = ctypes.c_int
+        L.sb_gin_agg_tile_rows.argtypes = [ctypes.c_int32]
+        L.sb_linear_wgrad_workspace_floats.restype = ctypes.c_int64
+        for name, sig in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = [_CT[c] for c in sig]
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(list(_SIGNATURES) + ["sb_last_error", "sb_abi_version", "sb_device_sm_count", "sb_gin_agg_tile_rows",
+                                       "sb_linear_wgrad_workspace_floats"])
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke an entry point on torch's current stream; raises RuntimeError(sb_last_error()) on failure."""
+    L = lib()
+    rc = getattr(L, name)(*args, stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {L.sb_last_error().decode()}")
+
+
+launch_count = 0  # number of C-ABI calls issued (each enqueues >= 1 kernel); bench.py reports it
+_profile = None   # None = off; else list of (tag, start_event, end_event) on torch's current stream
+
+
+def counted_call(name, *args):
+    global launch_count
+    launch_count += 1
+    if _profile is None:
+        call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(name, *args)
+    e1.record()
+    _profile.append((_profile_tag(name, args), e0, e1))
+
+
+def _profile_tag(name, args):
+    if name == "sb_gin_agg":  # (.., R, B, k, masked, S, ld, tile_rows, force_generic): split by row width / path
+        return f"sb_gin_agg[ld={args[16]}{',generic' if args[18] else ''}{',bwd' if args[2] or args[3] else ''}]"
+    return name
+
+
+def profile_start():
+    global _profile
+    _profile = []
+
+
+def profile_stop():
+    """-> {tag: (calls, total_ms)} measured with CUDA events on the launching stream."""
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for tag, e0, e1 in rec or []:
+        c, t = out.get(tag, (0, 0.0))
+        out[tag] = (c + 1, t + e0.elapsed_time(e1))
+    return out

@@ -1,0 +1,418 @@
+// K3/K4 — BatchNorm over the valid slot rows (per sign pass) and the element-wise glue of a GIN layer.
+// Replaces MaskedBN's `x[mask] = bn(x[mask])` gather/scatter copies and the `x[~mask] = 0` index_put_ bookkeeping
+// (Alchemy/sign_net/model_utils/masked_layers.py:13-20,59-60; sign_net.py:38-43): on the ragged slot-row layout the
+// statistics are plain column sums (accumulated in fp64 by the producing Linear's epilogue, see linear.cu), the
+// normalisation collapses to a per-(sign, channel) affine a*x + c that is applied in the consumer's prologue, and only
+// the residual stream X_{l+1} = relu(a*Y + c) + X_l is materialised.
+//
+// Numerics follow nn.BatchNorm1d: biased variance for normalisation, unbiased for the running buffer, eps 1e-5,
+// momentum 0.1, running statistics updated once per sign pass in +v, -v order (sign_net.py:113).
+#include "common.cuh"
+#include "../../include/signnet_b200.h"
+
+#define EW_THREADS 256
+
+// ------------------------------------------------------------------------------------------------------- finalize
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, long long M, int G, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                   float eps, int training, float* __restrict__ a, float* __restrict__ c,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= C) return;
+  const double gm = gamma ? (double)gamma[ch] : 1.0, bt = beta ? (double)beta[ch] : 0.0;
+  for (int g = 0; g < G; ++g) {
+    double mean, var;
+    if (training) {
+      const double s = stats[((long long)g * 2 + 0) * C + ch], q = stats[((long long)g * 2 + 1) * C + ch];
+      mean = s / (double)M;
+      var = q / (double)M - mean * mean;
+      if (var < 0.0) var = 0.0;
+      if (running_mean) {
+        const double unb = (M > 1) ? var * ((double)M / (double)(M - 1)) : var;
+        running_mean[ch] = (float)((1.0 - (double)momentum) * (double)running_mean[ch] + (double)momentum * mean);
+        running_var[ch] = (float)((1.0 - (double)momentum) * (double)running_var[ch] + (double)momentum * unb);
+      }
+    } else {
+      mean = (double)running_mean[ch];
+      var = (double)running_var[ch];
+    }
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    const double av = gm * rstd;
+    a[(long long)g * C + ch] = (float)av;
+    c[(long long)g * C + ch] = (float)(bt - mean * av);
+    if (mean_out) mean_out[(long long)g * C + ch] = (float)mean;
+    if (rstd_out) rstd_out[(long long)g * C + ch] = (float)rstd;
+  }
+}
+
+extern "C" int sb_bn_finalize(const double* stats, int64_t M, int32_t G, int32_t C, const float* gamma,
+                              const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                              int32_t training, float* a, float* c, float* mean, float* rstd, void* stream) {
+  SB_CHECK_ARG(G >= 1 && C >= 1 && a && c, "sb_bn_finalize: bad args");
+  SB_CHECK_ARG(training ? (stats != nullptr && M >= 1) : (running_mean && running_var),
+               "sb_bn_finalize: training needs stats and M>=1, eval needs running statistics");
+  bn_finalize_kernel<<<(unsigned)sb_ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+      stats, M, G, C, gamma, beta, running_mean, running_var, momentum, eps, training, a, c, mean, rstd);
+  SB_CHECK_LAUNCH("sb_bn_finalize");
+  return SB_OK;
+}
+
+// ----------------------------------------------------------------------------------- per-(group, channel) column sums
+// stats[g, 0, c] += sum_r x[g, r, c] ; stats[g, 1, c] += sum_r x[g, r, c]^2     (for tensors no Linear epilogue saw)
+template <int VEC>
+__global__ void __launch_bounds__(EW_THREADS) col_stats_kernel(const float* __restrict__ x, long long ld, long long R,
+                                                               int C, double* __restrict__ stats) {
+  extern __shared__ double red[];  // [rows_per_iter][2][ldv*VEC]
+  const int ldv = (int)(ld / VEC);
+  const int rpi = EW_THREADS / ldv;
+  const int g = blockIdx.y;
+  const int cg = threadIdx.x % ldv, rs = threadIdx.x / ldv;
+  float s[VEC], q[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
+  if (rs < rpi) {
+    for (long long r = (long long)blockIdx.x * rpi + rs; r < R; r += (long long)gridDim.x * rpi) {
+      const float* p = x + ((long long)g * R + r) * ld + cg * VEC;
+      float v[VEC];
+      if constexpr (VEC == 4) {
+        const float4 t = ldg4(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+        v[0] = __ldg(p);
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+    }
+  }
+  const int W = ldv * VEC;
+  if (rs < rpi) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      red[(rs * 2 + 0) * W + cg * VEC + j] = (double)s[j];
+      red[(rs * 2 + 1) * W + cg * VEC + j] = (double)q[j];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * W; idx += EW_THREADS) {
+    const int which = idx / W, col = idx % W;
+    if (col < C) {
+      double t = 0.0;
+      for (int r = 0; r < rpi; ++r) t += red[(r * 2 + which) * W + col];
+      atomicAdd(stats + ((long long)g * 2 + which) * C + col, t);
+    }
+  }
+}
+
+extern "C" int sb_col_stats(const float* x, int64_t ld, int64_t R, int32_t G, int32_t C, double* stats,
+                            void* stream) {
+  SB_CHECK_ARG(R >= 0 && G >= 1 && C >= 1 && ld >= C && ld <= 1024, "sb_col_stats: bad sizes");
+  if (R == 0) return SB_OK;
+  const bool vec = (ld % 4 == 0) && ((uintptr_t)x % 16 == 0);
+  const int VEC = vec ? 4 : 1;
+  const int ldv = (int)(ld / VEC);
+  SB_CHECK_ARG(ldv <= EW_THREADS, "sb_col_stats: row too wide");
+  const int rpi = EW_THREADS / ldv;
+  long long blocks = sb_ceil_div(R, (long long)rpi * 8);
+  const long long cap = (long long)sb_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  dim3 grid((unsigned)blocks, (unsigned)G);
+  const size_t smem = (size_t)rpi * 2 * ldv * VEC * sizeof(double);
+  if (vec) col_stats_kernel<4><<<grid, EW_THREADS, smem, (cudaStream_t)stream>>>(x, ld, R, C, stats);
+  else col_stats_kernel<1><<<grid, EW_THREADS, smem, (cudaStream_t)stream>>>(x, ld, R, C, stats);
+  SB_CHECK_LAUNCH("sb_col_stats");
+  return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------- forward: affine(+relu)(+res)
+// out[g, r, c] = act(a[g,c] * y[g,r,c] + c[g,c]) + res[g,r,c]      (pad columns C..ld-1 -> 0)
+__global__ void __launch_bounds__(EW_THREADS) affine_act_res_kernel(const float* __restrict__ y,
+                                                                    const float* __restrict__ pa,
+                                                                    const float* __restrict__ pc,
+                                                                    const float* __restrict__ res,
+                                                                    float* __restrict__ out, long long ld,
+                                                                    long long R, int G, int C, int relu) {
+  const long long ld4 = ld >> 2;
+  const long long total = (long long)G * R * ld4;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / ld4;
+    const int c4 = (int)(t - row * ld4);
+    const int g = (int)(row / R);
+    const float4 v = ldg4(y + t * 4);
+    float in[4] = {v.x, v.y, v.z, v.w}, o[4];
+    float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (res) rr = ldg4(res + t * 4);
+    const float rv[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = c4 * 4 + j;
+      if (col < C) {
+        float u = pa ? fmaf(__ldg(pa + (long long)g * C + col), in[j], __ldg(pc + (long long)g * C + col)) : in[j];
+        if (relu) u = fmaxf(u, 0.f);
+        o[j] = u + rv[j];
+      } else {
+        o[j] = 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(out + t * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+extern "C" int sb_affine_act_res(const float* y, const float* pa, const float* pc, const float* res, float* out,
+                                 int64_t ld, int64_t R, int32_t G, int32_t C, int32_t relu, void* stream) {
+  SB_CHECK_ARG(ld % 4 == 0 && ld >= C && G >= 1, "sb_affine_act_res: ld must be a multiple of 4 and >= C");
+  SB_CHECK_ARG((pa == nullptr) == (pc == nullptr), "sb_affine_act_res: pa/pc must come together");
+  if (R == 0) return SB_OK;
+  const long long total = (long long)G * R * (ld / 4);
+  long long blocks = sb_ceil_div(total, EW_THREADS * 4);
+  const long long cap = (long long)sb_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  affine_act_res_kernel<<<(unsigned)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>(y, pa, pc, res, out, ld, R, G, C,
+                                                                                   relu);
+  SB_CHECK_LAUNCH("sb_affine_act_res");
+  return SB_OK;
+}
+
+// --------------------------------------------------------------------------- backward: relu mask + BN reductions
+// dz = gout * [a*y + c > 0]  (relu) or gout;  s1[g,c] += sum_r dz ;  s2[g,c] += sum_r dz * (y - mean) * rstd.
+// dz may alias gout (in place).
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const float* gout, const float* __restrict__ y,
+                                                                   const float* __restrict__ pa,
+                                                                   const float* __restrict__ pc,
+                                                                   const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd, float* dz,
+                                                                   long long ld, long long R, int C, int relu,
+                                                                   double* __restrict__ stats) {
+  extern __shared__ double red[];
+  const int ldv = (int)(ld >> 2);
+  const int rpi = EW_THREADS / ldv;
+  const int g = blockIdx.y;
+  const int cg = threadIdx.x % ldv, rs = threadIdx.x / ldv;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rs < rpi) {
+    float a4[4], c4[4], m4[4], r4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = cg * 4 + j;
+      const bool ok = col < C;
+      a4[j] = ok ? __ldg(pa + (long long)g * C + col) : 0.f;
+      c4[j] = ok ? __ldg(pc + (long long)g * C + col) : 0.f;
+      m4[j] = ok ? __ldg(mean + (long long)g * C + col) : 0.f;
+      r4[j] = ok ? __ldg(rstd + (long long)g * C + col) : 0.f;
+    }
+    for (long long r = (long long)blockIdx.x * rpi + rs; r < R; r += (long long)gridDim.x * rpi) {
+      const long long off = ((long long)g * R + r) * ld + cg * 4;
+      const float4 gv = *reinterpret_cast<const float4*>(gout + off);
+      const float4 yv = ldg4(y + off);
+      const float gi[4] = {gv.x, gv.y, gv.z, gv.w}, yi[4] = {yv.x, yv.y, yv.z, yv.w};
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float d = gi[j];
+        if (relu && !(fmaf(a4[j], yi[j], c4[j]) > 0.f)) d = 0.f;
+        if (cg * 4 + j >= C) d = 0.f;
+        o[j] = d;
+        s1[j] += d;
+        s2[j] = fmaf(d, (yi[j] - m4[j]) * r4[j], s2[j]);
+      }
+      if (dz) *reinterpret_cast<float4*>(dz + off) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  const int W = ldv * 4;
+  if (rs < rpi) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[(rs * 2 + 0) * W + cg * 4 + j] = (double)s1[j];
+      red[(rs * 2 + 1) * W + cg * 4 + j] = (double)s2[j];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * W; idx += EW_THREADS) {
+    const int which = idx / W, col = idx % W;
+    if (col < C) {
+      double t = 0.0;
+      for (int r = 0; r < rpi; ++r) t += red[(r * 2 + which) * W + col];
+      atomicAdd(stats + ((long long)g * 2 + which) * C + col, t);
+    }
+  }
+}
+
+extern "C" int sb_bn_bwd_reduce(const float* gout, const float* y, const float* pa, const float* pc,
+                                const float* mean, const float* rstd, float* dz, int64_t ld, int64_t R, int32_t G,
+                                int32_t C, int32_t relu, double* stats, void* stream) {
+  SB_CHECK_ARG(ld % 4 == 0 && ld >= C && ld / 4 <= EW_THREADS && G >= 1, "sb_bn_bwd_reduce: bad leading dim");
+  SB_CHECK_ARG(gout && y && pa && pc && mean && rstd && stats, "sb_bn_bwd_reduce: null argument");
+  if (R == 0) return SB_OK;
+  const int ldv = (int)(ld / 4);
+  const int rpi = EW_THREADS / ldv;
+  long long blocks = sb_ceil_div(R, (long long)rpi * 8);
+  const long long cap = (long long)sb_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  dim3 grid((unsigned)blocks, (unsigned)G);
+  const size_t smem = (size_t)rpi * 2 * ldv * 4 * sizeof(double);
+  bn_bwd_reduce_kernel<<<grid, EW_THREADS, smem, (cudaStream_t)stream>>>(gout, y, pa, pc, mean, rstd, dz, ld, R, C,
+                                                                        relu, stats);
+  SB_CHECK_LAUNCH("sb_bn_bwd_reduce");
+  return SB_OK;
+}
+
+// dgamma (+)= sum_g s2[g], dbeta (+)= sum_g s1[g]; coefficient vectors of  dY = al*dZ + be*Y + ga :
+//   training:  al = a, be = -a*rstd*m2, ga = -a*m1 + a*rstd*m2*mean      (m1 = s1/M, m2 = s2/M)
+//   eval:      al = a, be = 0,          ga = 0
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, long long M, int G, int C,
+                                       const float* __restrict__ pa, const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, int training, int accumulate,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ al,
+                                       float* __restrict__ be, float* __restrict__ ga) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= C) return;
+  double dg = 0.0, db = 0.0;
+  for (int g = 0; g < G; ++g) {
+    const double s1 = stats[((long long)g * 2 + 0) * C + ch], s2 = stats[((long long)g * 2 + 1) * C + ch];
+    dg += s2;
+    db += s1;
+    const double a = (double)pa[(long long)g * C + ch];
+    double bev = 0.0, gav = 0.0;
+    if (training) {
+      const double m1 = s1 / (double)M, m2 = s2 / (double)M;
+      const double rs = (double)rstd[(long long)g * C + ch], mu = (double)mean[(long long)g * C + ch];
+      bev = -a * rs * m2;
+      gav = -a * m1 + a * rs * m2 * mu;
+    }
+    al[(long long)g * C + ch] = (float)a;
+    be[(long long)g * C + ch] = (float)bev;
+    ga[(long long)g * C + ch] = (float)gav;
+  }
+  if (dgamma) dgamma[ch] = accumulate ? dgamma[ch] + (float)dg : (float)dg;
+  if (dbeta) dbeta[ch] = accumulate ? dbeta[ch] + (float)db : (float)db;
+}
+
+extern "C" int sb_bn_bwd_finalize(const double* stats, int64_t M, int32_t G, int32_t C, const float* pa,
+                                  const float* mean, const float* rstd, int32_t training, int32_t accumulate,
+                                  float* dgamma, float* dbeta, float* al, float* be, float* ga, void* stream) {
+  SB_CHECK_ARG(stats && pa && mean && rstd && al && be && ga && M >= 1, "sb_bn_bwd_finalize: null argument");
+  bn_bwd_finalize_kernel<<<(unsigned)sb_ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+      stats, M, G, C, pa, mean, rstd, training, accumulate, dgamma, dbeta, al, be, ga);
+  SB_CHECK_LAUNCH("sb_bn_bwd_finalize");
+  return SB_OK;
+}
+
+// out = al[g,c]*t1 + be[g,c]*t2 + ga[g,c]   (out may alias t1; pad columns -> 0)
+__global__ void __launch_bounds__(EW_THREADS) affine2_kernel(const float* t1, const float* __restrict__ t2,
+                                                             const float* __restrict__ al,
+                                                             const float* __restrict__ be,
+                                                             const float* __restrict__ ga, float* out, long long ld,
+                                                             long long R, int G, int C) {
+  const long long ld4 = ld >> 2;
+  const long long total = (long long)G * R * ld4;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / ld4;
+    const int c4 = (int)(t - row * ld4);
+    const int g = (int)(row / R);
+    const float4 u = *reinterpret_cast<const float4*>(t1 + t * 4);
+    const float4 v = ldg4(t2 + t * 4);
+    const float ui[4] = {u.x, u.y, u.z, u.w}, vi[4] = {v.x, v.y, v.z, v.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = c4 * 4 + j;
+      if (col < C) {
+        const long long p = (long long)g * C + col;
+        o[j] = fmaf(__ldg(al + p), ui[j], fmaf(__ldg(be + p), vi[j], __ldg(ga + p)));
+      } else {
+        o[j] = 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(out + t * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+extern "C" int sb_affine2(const float* t1, const float* t2, const float* al, const float* be, const float* ga,
+                          float* out, int64_t ld, int64_t R, int32_t G, int32_t C, void* stream) {
+  SB_CHECK_ARG(ld % 4 == 0 && ld >= C && G >= 1, "sb_affine2: ld must be a multiple of 4 and >= C");
+  if (R == 0) return SB_OK;
+  const long long total = (long long)G * R * (ld / 4);
+  long long blocks = sb_ceil_div(total, EW_THREADS * 4);
+  const long long cap = (long long)sb_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  affine2_kernel<<<(unsigned)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>(t1, t2, al, be, ga, out, ld, R, G, C);
+  SB_CHECK_LAUNCH("sb_affine2");
+  return SB_OK;
+}
+
+// ------------------------------------------------------------------------------ slot / sign reduction for rho
+// out[node, c] = sum_s sum_{j < k_b} x[s, row(b, j, i), c]      ("sum over the k eigenvector slots and both signs",
+// sign_net.py:113 + :70 / deepsigns.py:72-81).  One warp per node, fixed summation order (s outer, j inner).
+__global__ void __launch_bounds__(256) slot_sum_fwd_kernel(const float* __restrict__ x, long long ld, long long R,
+                                                           int S, const int64_t* __restrict__ batch,
+                                                           const int32_t* __restrict__ gp,
+                                                           const int64_t* __restrict__ row_ptr, long long N, int k,
+                                                           int masked, int k_limit_by_n, float* __restrict__ out,
+                                                           long long ldo, int C) {
+  const long long node = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (node >= N) return;
+  const int b = (int)batch[node];
+  const int n = gp[b + 1] - gp[b];
+  int kb = masked ? (n < k ? n : k) : k;
+  if (k_limit_by_n && kb > n) kb = n;  // DGL masked variant: slots >= n_b are zeroed before the sum
+  const int li = (int)(node - gp[b]);
+  const long long r0 = row_ptr[b] + li;
+  for (int c = lane; c < (int)ldo; c += 32) {
+    float acc = 0.f;
+    if (c < C) {
+      for (int s = 0; s < S; ++s)
+        for (int j = 0; j < kb; ++j) acc += __ldg(x + ((long long)s * R + r0 + (long long)j * n) * ld + c);
+    }
+    out[node * ldo + c] = acc;
+  }
+}
+extern "C" int sb_slot_sum_fwd(const float* x, int64_t ld, int64_t R, int32_t S, const int64_t* batch,
+                               const int32_t* graph_ptr, const int64_t* row_ptr, int64_t N, int32_t k,
+                               int32_t masked, int32_t limit_by_n, float* out, int64_t ldo, int32_t C,
+                               void* stream) {
+  if (N == 0) return SB_OK;
+  slot_sum_fwd_kernel<<<(unsigned)sb_ceil_div(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, ld, R, S, batch, graph_ptr, row_ptr, N, k, masked, limit_by_n, out, ldo, C);
+  SB_CHECK_LAUNCH("sb_slot_sum_fwd");
+  return SB_OK;
+}
+
+// backward: gx[s, row(b,j,i), c] = gout[node, c] for contributing slots (0 for slots zeroed by limit_by_n)
+__global__ void __launch_bounds__(256) slot_sum_bwd_kernel(const float* __restrict__ gout, long long ldo,
+                                                           float* __restrict__ gx, long long ld, long long R, int S,
+                                                           const int64_t* __restrict__ batch,
+                                                           const int32_t* __restrict__ gp,
+                                                           const int64_t* __restrict__ row_ptr, long long N, int k,
+                                                           int masked, int k_limit_by_n, int C) {
+  const long long node = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (node >= N) return;
+  const int b = (int)batch[node];
+  const int n = gp[b + 1] - gp[b];
+  const int kb = masked ? (n < k ? n : k) : k;
+  int klive = kb;
+  if (k_limit_by_n && klive > n) klive = n;
+  const int li = (int)(node - gp[b]);
+  const long long r0 = row_ptr[b] + li;
+  for (int c = lane; c < (int)ld; c += 32) {
+    const float gv = (c < C) ? __ldg(gout + node * ldo + c) : 0.f;
+    for (int s = 0; s < S; ++s)
+      for (int j = 0; j < kb; ++j) gx[((long long)s * R + r0 + (long long)j * n) * ld + c] = (j < klive) ? gv : 0.f;
+  }
+}
+extern "C" int sb_slot_sum_bwd(const float* gout, int64_t ldo, float* gx, int64_t ld, int64_t R, int32_t S,
+                               const int64_t* batch, const int32_t* graph_ptr, const int64_t* row_ptr, int64_t N,
+                               int32_t k, int32_t masked, int32_t limit_by_n, int32_t C, void* stream) {
+  if (N == 0) return SB_OK;
+  slot_sum_bwd_kernel<<<(unsigned)sb_ceil_div(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      gout, ldo, gx, ld, R, S, batch, graph_ptr, row_ptr, N, k, masked, limit_by_n, C);
+  SB_CHECK_LAUNCH("sb_slot_sum_bwd");
+  return SB_OK;
+}

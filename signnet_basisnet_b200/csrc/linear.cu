@@ -1,0 +1,581 @@
+// K2 — the dense per-row contractions of the path (the two Linears inside every GIN layer, rho's MLP, the predictor's
+// MLPs) as weight-stationary, persistent fp32 kernels with the neighbouring element-wise work fused in:
+//   prologue  (on load of the activation tile): none | BatchNorm-affine | BatchNorm-affine + ReLU
+//   epilogue  (on the accumulator tile)       : + bias | ReLU | per-(group, channel) sum / sum-of-squares for the
+//                                               BatchNorm that follows (no second pass over the activations)
+// Replaces nn.Linear + the `x[~mask] = 0` / `x[mask] = bn(x[mask])` bookkeeping of MaskedMLP
+// (Alchemy/sign_net/model_utils/masked_layers.py:54-64) and layers/mlp.py:37-56: on the ragged slot-row layout every
+// row is valid, so the masks disappear.
+//
+// fp32 FFMA on purpose: BASELINE.json's parity bar is 1e-5 relative in fp32, which a single-pass TF32/bf16 tensor-core
+// contraction does not meet.  The weight matrix (<= 128 x 128) stays resident in shared memory for the lifetime of a
+// persistent CTA; activation tiles are double-buffered through registers so the prologue transform is applied once
+// per element.
+#include "common.cuh"
+#include "../../include/signnet_b200.h"
+
+#define LIN_BM 128
+#define LIN_BK 32
+#define LIN_BKP 36
+#define LIN_THREADS 256
+#define LIN_MAXG 2
+
+struct LinArgs {
+  const float* x;
+  long long ldx;
+  const float* w;
+  long long w_rs, w_cs;
+  const float* bias;
+  float* y;
+  long long ldy;
+  long long R;
+  int G, K, N, KP;
+  int pro;
+  const float* pa;
+  const float* pc;
+  int relu;
+  double* stats;
+  int accumulate;
+  int xvec, yvec;  // 128-bit access allowed on x / y
+  int ycols;       // columns of y this launch may write (>= N; the tail N..ycols-1 is zero-filled)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(LIN_THREADS, (BN == 64) ? 2 : 1) linear_fwd_kernel(const LinArgs a) {
+  constexpr int NT = BN / 16;   // output columns per thread (4 or 8)
+  constexpr int NV = NT / 4;    // float4 column groups per thread
+  extern __shared__ __align__(16) float smem[];
+  float* Ws = smem;                                  // [KP][BN]
+  float* As = Ws + (size_t)a.KP * BN;                // [2][LIN_BM][LIN_BKP]
+  double* sacc = reinterpret_cast<double*>(As + 2 * LIN_BM * LIN_BKP);  // [LIN_MAXG][2][BN]
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int K = a.K, N = a.N, KP = a.KP;
+
+  // ---- stage the weight: Ws[k][n] = W[n, k], zero padded
+  for (int idx = tid; idx < KP * BN; idx += LIN_THREADS) {
+    int k, n;
+    if (a.w_cs == 1) { n = idx / KP; k = idx - n * KP; } else { k = idx / BN; n = idx - k * BN; }
+    float v = 0.f;
+    if (k < K && n < N) v = __ldg(a.w + (long long)n * a.w_rs + (long long)k * a.w_cs);
+    Ws[k * BN + n] = v;
+  }
+  if (a.stats)
+    for (int idx = tid; idx < LIN_MAXG * 2 * BN; idx += LIN_THREADS) sacc[idx] = 0.0;
+
+  const long long tpg = (a.R + LIN_BM - 1) / LIN_BM;  // tiles per group
+  const long long ntiles = tpg * a.G;
+  const int nchunks = KP / LIN_BK;
+
+  float4 pre[4];
+  auto load_chunk = [&](long long tile, int chunk) {
+    const int g = (int)(tile / tpg);
+    const long long row0 = (tile - (long long)g * tpg) * LIN_BM;
+    const int rows = (int)((a.R - row0 < LIN_BM) ? (a.R - row0) : LIN_BM);
+    const long long base = (long long)g * a.R + row0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int f = tid + LIN_THREADS * q;
+      const int row = f >> 3, c4 = f & 7;
+      const int col = chunk * LIN_BK + c4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows && col < K) {
+        const float* p = a.x + (base + row) * a.ldx + col;
+        if (a.xvec) {
+          v = ldg4(p);
+        } else {
+          v.x = __ldg(p);
+          if (col + 1 < K) v.y = __ldg(p + 1);
+          if (col + 2 < K) v.z = __ldg(p + 2);
+          if (col + 3 < K) v.w = __ldg(p + 3);
+        }
+        if (a.pro) {
+          const float* pa = a.pa + (long long)g * K + col;
+          const float* pc = a.pc + (long long)g * K + col;
+          float t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (col + j < K) {
+              float u = fmaf(__ldg(pa + j), t[j], __ldg(pc + j));
+              t[j] = (a.pro == 2) ? fmaxf(u, 0.f) : u;
+            } else {
+              t[j] = 0.f;
+            }
+          }
+          v = make_float4(t[0], t[1], t[2], t[3]);
+        } else {
+          if (col + 1 >= K) v.y = 0.f;
+          if (col + 2 >= K) v.z = 0.f;
+          if (col + 3 >= K) v.w = 0.f;
+        }
+      }
+      pre[q] = v;
+    }
+  };
+  auto store_chunk = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int f = tid + LIN_THREADS * q;
+      const int row = f >> 3, c4 = f & 7;
+      *reinterpret_cast<float4*>(As + ((size_t)buf * LIN_BM + row) * LIN_BKP + c4 * 4) = pre[q];
+    }
+  };
+
+  float acc[8][NT];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
+
+  long long tile = blockIdx.x;
+  int chunk = 0, buf = 0;
+  if (tile < ntiles) {
+    load_chunk(tile, 0);
+    store_chunk(0);
+  }
+  __syncthreads();
+
+  while (tile < ntiles) {
+    long long ntile = tile;
+    int nchunk = chunk + 1;
+    if (nchunk == nchunks) { nchunk = 0; ntile = tile + gridDim.x; }
+    const bool has_next = ntile < ntiles;
+    if (has_next) load_chunk(ntile, nchunk);
+
+    const float* Ab = As + (size_t)buf * LIN_BM * LIN_BKP;
+    const float* Wb = Ws + (size_t)chunk * LIN_BK * BN;
+#pragma unroll
+    for (int kk = 0; kk < LIN_BK; kk += 4) {
+      float4 av[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) av[i] = *reinterpret_cast<const float4*>(Ab + (ty + 16 * i) * LIN_BKP + kk);
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        float wv[NT];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const float4 w4 = *reinterpret_cast<const float4*>(Wb + (kk + k4) * BN + v * 64 + tx * 4);
+          wv[v * 4 + 0] = w4.x; wv[v * 4 + 1] = w4.y; wv[v * 4 + 2] = w4.z; wv[v * 4 + 3] = w4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float aval = (k4 == 0) ? av[i].x : (k4 == 1) ? av[i].y : (k4 == 2) ? av[i].z : av[i].w;
+#pragma unroll
+          for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(aval, wv[j], acc[i][j]);
+        }
+      }
+    }
+
+    if (has_next) store_chunk(buf ^ 1);
+
+    if (chunk == nchunks - 1) {
+      // ---------------------------------------------------------------- epilogue for this row tile
+      const int g = (int)(tile / tpg);
+      const long long row0 = (tile - (long long)g * tpg) * LIN_BM;
+      const int rows = (int)((a.R - row0 < LIN_BM) ? (a.R - row0) : LIN_BM);
+      const long long base = (long long)g * a.R + row0;
+      float ssum[NT], ssq[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) ssum[j] = 0.f, ssq[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = ty + 16 * i;
+        if (row < rows) {
+          float* yrow = a.y + (base + row) * a.ldy;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const int col0 = v * 64 + tx * 4;
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int col = col0 + j;
+              float t = acc[i][v * 4 + j];
+              if (col < N) {
+                if (a.bias) t += __ldg(a.bias + col);
+                if (a.accumulate) t += yrow[col];
+                if (a.relu) t = fmaxf(t, 0.f);
+                ssum[v * 4 + j] += t;
+                ssq[v * 4 + j] = fmaf(t, t, ssq[v * 4 + j]);
+              } else {
+                t = 0.f;
+              }
+              o[j] = t;
+            }
+            if (a.yvec) {
+              if (col0 < a.ycols) *reinterpret_cast<float4*>(yrow + col0) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col0 + j < a.ycols) yrow[col0 + j] = o[j];
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
+      }
+      if (a.stats) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 16);
+          ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 16);
+        }
+        if ((tid & 31) < 16) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int col = v * 64 + tx * 4 + j;
+              if (col < N) {
+                atomicAdd(&sacc[(g * 2 + 0) * BN + col], (double)ssum[v * 4 + j]);
+                atomicAdd(&sacc[(g * 2 + 1) * BN + col], (double)ssq[v * 4 + j]);
+              }
+            }
+        }
+      }
+    }
+    __syncthreads();
+    buf ^= 1;
+    tile = ntile;
+    chunk = nchunk;
+  }
+
+  if (a.stats) {
+    __syncthreads();
+    for (int idx = tid; idx < a.G * 2 * BN; idx += LIN_THREADS) {
+      const int col = idx % BN, gj = idx / BN;
+      if (col < N && sacc[idx] != 0.0) atomicAdd(a.stats + (long long)gj * N + col, sacc[idx]);
+    }
+  }
+}
+
+static size_t lin_smem_bytes(int KP, int BN) {
+  return ((size_t)KP * BN + 2 * LIN_BM * LIN_BKP) * sizeof(float) + (size_t)LIN_MAXG * 2 * BN * sizeof(double);
+}
+
+template <int BN>
+static int launch_linear(const LinArgs& a, cudaStream_t st) {
+  static size_t configured = 0;
+  const size_t smem = lin_smem_bytes(a.KP, BN);
+  if (smem > configured) {
+    SB_CUDA(cudaFuncSetAttribute(linear_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)lin_smem_bytes(128, BN)));
+    configured = lin_smem_bytes(128, BN);
+  }
+  const long long ntiles = sb_ceil_div(a.R, LIN_BM) * a.G;
+  long long grid = (long long)sb_num_sms() * ((BN == 64) ? 2 : 1);
+  if (grid > ntiles) grid = ntiles;
+  linear_fwd_kernel<BN><<<(unsigned)grid, LIN_THREADS, smem, st>>>(a);
+  SB_CHECK_LAUNCH("sb_linear_fwd");
+  return SB_OK;
+}
+
+// y[g*R + r, n] (+)= sum_k f(x[g*R + r, k]) * W[n, k] + bias[n]   for n < N; columns N..ldy-1 of y are zero-filled.
+extern "C" int sb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t w_rs, int64_t w_cs,
+                             const float* bias, float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N,
+                             int32_t pro, const float* pa, const float* pc, int32_t relu, double* stats,
+                             int32_t accumulate, void* stream) {
+  SB_CHECK_ARG(R >= 0 && G >= 1 && G <= LIN_MAXG && K >= 1 && N >= 1, "sb_linear_fwd: bad sizes R=%lld G=%d K=%d N=%d",
+               (long long)R, G, K, N);
+  SB_CHECK_ARG(ldx >= K && ldy >= N, "sb_linear_fwd: leading dims too small");
+  SB_CHECK_ARG(pro >= 0 && pro <= 2 && (pro == 0 || (pa && pc)), "sb_linear_fwd: bad prologue");
+  if (R == 0) return SB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  // Host-side blocking over N (<= 128 per launch) and K (<= 128 per launch, accumulating).
+  for (int n0 = 0; n0 < N; n0 += 128) {
+    const int nn = (N - n0 < 128) ? (N - n0) : 128;
+    for (int k0 = 0; k0 < K; k0 += 128) {
+      const int kk = (K - k0 < 128) ? (K - k0) : 128;
+      const bool last_k = (k0 + 128 >= K);
+      LinArgs a;
+      a.x = x + k0; a.ldx = ldx;
+      a.w = w + (long long)n0 * w_rs + (long long)k0 * w_cs; a.w_rs = w_rs; a.w_cs = w_cs;
+      a.bias = (last_k && bias) ? bias + n0 : nullptr;
+      a.y = y + n0;
+      a.ldy = ldy;
+      a.R = R; a.G = G; a.K = kk; a.N = nn;
+      a.KP = (int)sb_ceil_div(kk, LIN_BK) * LIN_BK;
+      a.pro = pro; a.pa = pa ? pa + k0 : nullptr; a.pc = pc ? pc + k0 : nullptr;
+      a.relu = last_k ? relu : 0;
+      a.stats = last_k ? (stats ? stats + n0 : nullptr) : nullptr;
+      a.accumulate = (k0 > 0) ? 1 : accumulate;
+      SB_CHECK_ARG(!(pro && K > 128), "sb_linear_fwd: prologue with K > 128 unsupported");
+      SB_CHECK_ARG(!(stats && N > 128), "sb_linear_fwd: stats with N > 128 unsupported");
+      a.xvec = (ldx % 4 == 0) && ((uintptr_t)a.x % 16 == 0);
+      a.yvec = (ldy % 4 == 0) && ((uintptr_t)a.y % 16 == 0);
+      const bool last_n = (n0 + 128 >= N);
+      a.ycols = last_n ? (int)((ldy - n0 < 128) ? (ldy - n0) : 128) : 128;
+      int rc = (nn <= 64 && a.ycols <= 64) ? launch_linear<64>(a, st) : launch_linear<128>(a, st);
+      if (rc != SB_OK) return rc;
+    }
+  }
+  return SB_OK;
+}
+
+// =====================================================================================================================
+// Weight gradient:  dW[n, k] = sum_rows g[row, n] * f(x[row, k]),  dbias[n] = sum_rows g[row, n]
+// (f = the same prologue as the forward, recomputed instead of stored).  Tall-skinny reduction: persistent CTAs each
+// own a strided subset of 32-row chunks, keep a full [BN x BK] partial in registers, write it once to a workspace and
+// a second tiny kernel adds the per-CTA partials in a fixed order (deterministic, no float atomics).
+// =====================================================================================================================
+#define WG_BR 32
+
+struct WgArgs {
+  const float* g;
+  long long ldg;
+  const float* x;
+  long long ldx;
+  long long R;
+  int G, N, K;
+  int pro;
+  const float* pa;
+  const float* pc;
+  float* part_w;   // [grid][BN][BK]
+  float* part_b;   // [grid][BN] or null
+  int gvec, xvec;
+};
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(LIN_THREADS, 1) linear_wgrad_kernel(const WgArgs a) {
+  constexpr int MI = BN / 16;          // dW rows (n) per thread
+  constexpr int NT = BK / 16;          // dW cols (k) per thread
+  constexpr int NV = NT / 4;
+  constexpr int GQ = BN / 32;          // float4 loads of g per thread per chunk
+  constexpr int XQ = BK / 32;          // float4 loads of x per thread per chunk
+  extern __shared__ __align__(16) float smem[];
+  float* Gt = smem;                                   // [2][BN][LIN_BKP]   (transposed: [n][row])
+  float* Xs = Gt + 2 * BN * LIN_BKP;                  // [2][WG_BR][BK]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, wrp = tid >> 5;
+  const int N = a.N, K = a.K;
+
+  const long long cpg = (a.R + WG_BR - 1) / WG_BR;
+  const long long nchunks = cpg * a.G;
+
+  float4 pg[GQ], px[XQ];
+  float dbs[GQ][4];
+#pragma unroll
+  for (int q = 0; q < GQ; ++q) dbs[q][0] = dbs[q][1] = dbs[q][2] = dbs[q][3] = 0.f;
+
+  auto load_chunk = [&](long long c) {
+    const int g = (int)(c / cpg);
+    const long long row0 = (c - (long long)g * cpg) * WG_BR;
+    const int rows = (int)((a.R - row0 < WG_BR) ? (a.R - row0) : WG_BR);
+    const long long base = (long long)g * a.R + row0;
+#pragma unroll
+    for (int q = 0; q < GQ; ++q) {  // g: lane -> row (transposed smem store is then conflict-free)
+      const int row = lane, c4 = wrp + 8 * q;
+      const int col = c4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows && col < N) {
+        const float* p = a.g + (base + row) * a.ldg + col;
+        if (a.gvec) {
+          v = ldg4(p);
+        } else {
+          v.x = __ldg(p);
+          if (col + 1 < N) v.y = __ldg(p + 1);
+          if (col + 2 < N) v.z = __ldg(p + 2);
+          if (col + 3 < N) v.w = __ldg(p + 3);
+        }
+        if (col + 1 >= N) v.y = 0.f;
+        if (col + 2 >= N) v.z = 0.f;
+        if (col + 3 >= N) v.w = 0.f;
+      }
+      pg[q] = v;
+    }
+#pragma unroll
+    for (int q = 0; q < XQ; ++q) {
+      const int f = tid + LIN_THREADS * q;
+      const int row = f / (BK / 4), c4 = f % (BK / 4);
+      const int col = c4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows && col < K) {
+        const float* p = a.x + (base + row) * a.ldx + col;
+        if (a.xvec) {
+          v = ldg4(p);
+        } else {
+          v.x = __ldg(p);
+          if (col + 1 < K) v.y = __ldg(p + 1);
+          if (col + 2 < K) v.z = __ldg(p + 2);
+          if (col + 3 < K) v.w = __ldg(p + 3);
+        }
+        float t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (col + j < K) {
+            if (a.pro) {
+              float u = fmaf(__ldg(a.pa + (long long)g * K + col + j), t[j], __ldg(a.pc + (long long)g * K + col + j));
+              t[j] = (a.pro == 2) ? fmaxf(u, 0.f) : u;
+            }
+          } else {
+            t[j] = 0.f;
+          }
+        }
+        v = make_float4(t[0], t[1], t[2], t[3]);
+      }
+      px[q] = v;
+    }
+  };
+  auto store_chunk = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < GQ; ++q) {
+      const int row = lane, c4 = wrp + 8 * q;
+      float* dst = Gt + ((size_t)buf * BN + c4 * 4) * LIN_BKP + row;
+      dst[0] = pg[q].x; dst[LIN_BKP] = pg[q].y; dst[2 * LIN_BKP] = pg[q].z; dst[3 * LIN_BKP] = pg[q].w;
+      dbs[q][0] += pg[q].x; dbs[q][1] += pg[q].y; dbs[q][2] += pg[q].z; dbs[q][3] += pg[q].w;
+    }
+#pragma unroll
+    for (int q = 0; q < XQ; ++q) {
+      const int f = tid + LIN_THREADS * q;
+      const int row = f / (BK / 4), c4 = f % (BK / 4);
+      *reinterpret_cast<float4*>(Xs + ((size_t)buf * WG_BR + row) * BK + c4 * 4) = px[q];
+    }
+  };
+
+  float acc[MI][NT];
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
+
+  long long c = blockIdx.x;
+  int buf = 0;
+  if (c < nchunks) {
+    load_chunk(c);
+    store_chunk(0);
+  }
+  __syncthreads();
+  while (c < nchunks) {
+    const long long nc = c + gridDim.x;
+    const bool has_next = nc < nchunks;
+    if (has_next) load_chunk(nc);
+    const float* Gb = Gt + (size_t)buf * BN * LIN_BKP;
+    const float* Xb = Xs + (size_t)buf * WG_BR * BK;
+#pragma unroll
+    for (int rr = 0; rr < WG_BR; rr += 4) {
+      float4 gv[MI];
+#pragma unroll
+      for (int i = 0; i < MI; ++i) gv[i] = *reinterpret_cast<const float4*>(Gb + (ty + 16 * i) * LIN_BKP + rr);
+#pragma unroll
+      for (int r4 = 0; r4 < 4; ++r4) {
+        float xv[NT];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const float4 x4 = *reinterpret_cast<const float4*>(Xb + (rr + r4) * BK + v * 64 + tx * 4);
+          xv[v * 4 + 0] = x4.x; xv[v * 4 + 1] = x4.y; xv[v * 4 + 2] = x4.z; xv[v * 4 + 3] = x4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const float gval = (r4 == 0) ? gv[i].x : (r4 == 1) ? gv[i].y : (r4 == 2) ? gv[i].z : gv[i].w;
+#pragma unroll
+          for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(gval, xv[j], acc[i][j]);
+        }
+      }
+    }
+    if (has_next) store_chunk(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+    c = nc;
+  }
+
+  float* pw = a.part_w + (size_t)blockIdx.x * BN * BK;
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      *reinterpret_cast<float4*>(pw + (size_t)(ty + 16 * i) * BK + v * 64 + tx * 4) =
+          make_float4(acc[i][v * 4 + 0], acc[i][v * 4 + 1], acc[i][v * 4 + 2], acc[i][v * 4 + 3]);
+  if (a.part_b) {
+#pragma unroll
+    for (int q = 0; q < GQ; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float t = warp_sum(dbs[q][j]);
+        if (lane == 0) a.part_b[(size_t)blockIdx.x * BN + (wrp + 8 * q) * 4 + j] = t;
+      }
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part_w, const float* __restrict__ part_b, int nparts,
+                                    int BN, int BK, int N, int K, float* __restrict__ dw, long long rs, long long cs,
+                                    float* __restrict__ db, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < N * K) {
+    const int n = idx / K, k = idx - n * K;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += part_w[((size_t)p * BN + n) * BK + k];
+    float* dst = dw + n * rs + k * cs;
+    *dst = accumulate ? (*dst + s) : s;
+  } else if (db != nullptr && idx < N * K + N) {
+    const int n = idx - N * K;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += part_b[(size_t)p * BN + n];
+    db[n] = accumulate ? (db[n] + s) : s;
+  }
+}
+
+template <int BN, int BK>
+static int launch_wgrad(WgArgs a, int N, int K, float* dw, long long rs, long long cs, float* db, int accumulate,
+                        float* workspace, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = ((size_t)2 * BN * LIN_BKP + 2 * WG_BR * BK) * sizeof(float);
+  if (!configured) {
+    SB_CUDA(cudaFuncSetAttribute(linear_wgrad_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const long long nchunks = sb_ceil_div(a.R, WG_BR) * a.G;
+  long long grid = sb_num_sms();
+  if (grid > nchunks) grid = nchunks;
+  a.part_w = workspace;
+  a.part_b = db ? workspace + (size_t)grid * BN * BK : nullptr;
+  linear_wgrad_kernel<BN, BK><<<(unsigned)grid, LIN_THREADS, smem, st>>>(a);
+  SB_CHECK_LAUNCH("sb_linear_wgrad");
+  const int total = N * K + (db ? N : 0);
+  wgrad_reduce_kernel<<<(unsigned)sb_ceil_div(total, 128), 128, 0, st>>>(a.part_w, a.part_b, (int)grid, BN, BK, N, K,
+                                                                        dw, rs, cs, db, accumulate);
+  SB_CHECK_LAUNCH("sb_linear_wgrad(reduce)");
+  return SB_OK;
+}
+
+extern "C" int64_t sb_linear_wgrad_workspace_floats(void) {
+  return (int64_t)sb_num_sms() * (128 * 128 + 128);
+}
+
+// dw[n*rs + k*cs] (+)= sum_{g,r} gy[g*R + r, n] * f(x[g*R + r, k]);  db[n] (+)= sum gy[., n]
+extern "C" int sb_linear_wgrad(const float* gy, int64_t ldg, const float* x, int64_t ldx, int64_t R, int32_t G,
+                               int32_t N, int32_t K, int32_t pro, const float* pa, const float* pc, float* dw,
+                               int64_t dw_rs, int64_t dw_cs, float* db, int32_t accumulate, float* workspace,
+                               void* stream) {
+  SB_CHECK_ARG(R >= 0 && G >= 1 && N >= 1 && K >= 1 && ldg >= N && ldx >= K, "sb_linear_wgrad: bad sizes");
+  SB_CHECK_ARG(pro >= 0 && pro <= 2 && (pro == 0 || (pa && pc)), "sb_linear_wgrad: bad prologue");
+  SB_CHECK_ARG(workspace != nullptr, "sb_linear_wgrad: workspace required");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R == 0) {
+    if (!accumulate) {
+      // empty batch: gradients are zero
+      for (int n = 0; n < N; ++n) SB_CUDA(cudaMemsetAsync(dw + n * dw_rs, 0, sizeof(float) * (dw_cs == 1 ? K : 1), st));
+      if (db) SB_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * N, st));
+    }
+    return SB_OK;
+  }
+  for (int n0 = 0; n0 < N; n0 += 128) {
+    const int nn = (N - n0 < 128) ? (N - n0) : 128;
+    for (int k0 = 0; k0 < K; k0 += 128) {
+      const int kk = (K - k0 < 128) ? (K - k0) : 128;
+      WgArgs a;
+      a.g = gy + n0; a.ldg = ldg; a.x = x + k0; a.ldx = ldx; a.R = R; a.G = G; a.N = nn; a.K = kk;
+      a.pro = pro; a.pa = pa ? pa + k0 : nullptr; a.pc = pc ? pc + k0 : nullptr;
+      SB_CHECK_ARG(!(pro && K > 128), "sb_linear_wgrad: prologue with K > 128 unsupported");
+      a.gvec = (ldg % 4 == 0) && ((uintptr_t)a.g % 16 == 0);
+      a.xvec = (ldx % 4 == 0) && ((uintptr_t)a.x % 16 == 0);
+      a.part_w = nullptr; a.part_b = nullptr;
+      float* dwp = dw + (long long)n0 * dw_rs + (long long)k0 * dw_cs;
+      float* dbp = (db && k0 == 0) ? db + n0 : nullptr;
+      int rc;
+      if (nn <= 64 && kk <= 64) rc = launch_wgrad<64, 64>(a, nn, kk, dwp, dw_rs, dw_cs, dbp, accumulate, workspace, st);
+      else if (nn <= 64) rc = launch_wgrad<64, 128>(a, nn, kk, dwp, dw_rs, dw_cs, dbp, accumulate, workspace, st);
+      else if (kk <= 64) rc = launch_wgrad<128, 64>(a, nn, kk, dwp, dw_rs, dw_cs, dbp, accumulate, workspace, st);
+      else rc = launch_wgrad<128, 128>(a, nn, kk, dwp, dw_rs, dw_cs, dbp, accumulate, workspace, st);
+      if (rc != SB_OK) return rc;
+    }
+  }
+  return SB_OK;
+}

@@ -25,3 +25,39 @@ def assert_grads_close(named_got, named_ref, tol, what=""):
         g = named_got.get(k)
         assert g is not None, f"{what}: no gradient for {k}"
         assert_close_rel(g, v, tol, floor=0.1 * gmax, what=f"{what} grad {k}")
+
+
+def slot_row_index(batch: torch.Tensor, k: int, masked: bool = True) -> torch.Tensor:
+    """CPU restatement of the slot-row layout (include/signnet_b200.h): idx[node, j] = row(b, j, i) or -1."""
+    import numpy as np
+
+    b = batch.cpu().numpy()
+    B = int(b.max()) + 1 if b.size else 0
+    n = np.bincount(b, minlength=B)
+    kb = np.minimum(n, k) if masked else np.full_like(n, k)
+    row_ptr = np.concatenate([[0], np.cumsum(n * kb)])
+    node_ptr = np.concatenate([[0], np.cumsum(n)])
+    idx = -np.ones((b.size, k), dtype=np.int64)
+    for g in range(B):
+        for j in range(int(kb[g])):
+            idx[node_ptr[g]:node_ptr[g + 1], j] = row_ptr[g] + j * n[g] + np.arange(n[g])
+    return torch.from_numpy(idx)
+
+
+def dense_to_rows(x_dense: torch.Tensor, idx: torch.Tensor, ld: int) -> torch.Tensor:
+    """[N, k, C] -> [R, ld] (zero padded columns), rows ordered by the slot-row layout."""
+    C = x_dense.shape[-1]
+    R = int(idx.max()) + 1
+    out = torch.zeros(R, ld, dtype=x_dense.dtype)
+    valid = idx >= 0
+    out[idx[valid], :C] = x_dense[valid]
+    return out
+
+
+def rows_to_dense(rows: torch.Tensor, idx: torch.Tensor, C: int) -> torch.Tensor:
+    """[R, ld] -> [N, k, C] with zeros in the padded slots."""
+    N, k = idx.shape
+    out = torch.zeros(N, k, C, dtype=rows.dtype)
+    valid = idx >= 0
+    out[valid] = rows[idx[valid], :C]
+    return out

@@ -1,0 +1,132 @@
+"""Parity of the CUDA SignNet path (modules -> autograd Functions -> C ABI) against the CPU oracle on seeded inputs:
+outputs and every parameter gradient within 1e-5 relative fp32 (BASELINE.json north_star), BatchNorm running buffers
+included."""
+import pytest
+import torch
+
+import restate
+from helpers import assert_close_rel, assert_grads_close, rows_to_dense, slot_row_index
+from signnet_basisnet_b200.synth import synth_batch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-5
+
+
+def _cpu_sd(module, leaf=True):
+    sd = {k: v.detach().cpu().clone() for k, v in module.state_dict().items()}
+    if leaf:
+        for k, v in sd.items():
+            if v.is_floating_point() and "running_" not in k:
+                v.requires_grad_(True)
+    return sd
+
+
+def _check_buffers(module, sd, what):
+    for name, buf in module.named_buffers():
+        if buf.is_floating_point():
+            assert_close_rel(buf.cpu(), sd[name], TOL, what=f"{what} buffer {name}")
+        else:
+            assert torch.equal(buf.cpu(), sd[name]), f"{what} buffer {name}: {buf} vs {sd[name]}"
+
+
+@pytest.mark.parametrize("shape,B,flavour,nhid,nl", [("alchemy", 24, "alchemy", 64, 3), ("zinc", 16, "alchemy", 128, 2),
+                                                     ("zinc", 12, "zinc", 95, 3), ("alchemy", 9, "zinc", 20, 4)])
+def test_phi_stack_forward_backward(shape, B, flavour, nhid, nl):
+    from signnet_basisnet_b200.layout import GraphIndex, pad4
+    from signnet_basisnet_b200.sign_net import GNN3d, build_phi_input
+
+    torch.manual_seed(0)
+    d = synth_batch(B, shape, seed=11)
+    phi = GNN3d(1, nhid, nl, flavour=flavour).to(DEV).train()
+    with torch.no_grad():  # non-trivial affine parameters / eps so every gradient path is exercised
+        for n_, p in phi.named_parameters():
+            if n_.endswith("bn.weight"):
+                p.uniform_(0.5, 1.5)
+            elif n_.endswith("bn.bias") or n_.endswith("eps"):
+                p.uniform_(-0.3, 0.3)
+    sd = _cpu_sd(phi)
+    _, eigV = restate.dense_list_evd(d.eigen_values, d.eigen_vectors, d.batch)
+    k = eigV.shape[1]
+    mask = restate.slot_mask(d.batch, k)
+    ref = restate.phi_pm(eigV, d.edge_index, mask, sd, "", nl, True)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1)) * mask.unsqueeze(-1)
+    (ref * w).sum().backward()
+
+    gi = GraphIndex(d.edge_index.to(DEV), d.batch.to(DEV), d.num_graphs)
+    sl = gi.slots_all(pad4(nhid))
+    assert sl.k == k
+    x0 = build_phi_input(gi, sl, d.eigen_vectors.to(DEV))
+    xr, sl = phi.forward_rows(x0, gi, k, True)
+    idx = slot_row_index(d.batch, k, True)
+    got = rows_to_dense(xr[0].cpu(), idx, nhid) + rows_to_dense(xr[1].cpu(), idx, nhid)
+    assert_close_rel(got, ref.detach(), TOL, what="phi(+v)+phi(-v)")
+    from helpers import dense_to_rows
+    w_rows = dense_to_rows(w, idx, pad4(nhid)).to(DEV)
+    (xr * w_rows.unsqueeze(0)).sum().backward()
+    assert_grads_close({n_: p.grad.cpu() for n_, p in phi.named_parameters() if p.grad is not None},
+                       {n_: v.grad for n_, v in sd.items() if v.requires_grad and v.grad is not None}, TOL, "phi")
+    _check_buffers(phi, sd, "phi")
+
+
+def test_phi_eval_mode_and_sign_invariance():
+    from signnet_basisnet_b200.layout import GraphIndex, pad4
+    from signnet_basisnet_b200.sign_net import GNN3d, build_phi_input
+
+    torch.manual_seed(3)
+    d = synth_batch(10, "zinc", seed=12)
+    phi = GNN3d(1, 32, 2).to(DEV)
+    with torch.no_grad():
+        for n_, b in phi.named_buffers():
+            if n_.endswith("running_mean"):
+                b.normal_(0, 0.2)
+            elif n_.endswith("running_var"):
+                b.uniform_(0.5, 2.0)
+    phi.eval()
+    sd = _cpu_sd(phi, leaf=False)
+    _, eigV = restate.dense_list_evd(d.eigen_values, d.eigen_vectors, d.batch)
+    k = eigV.shape[1]
+    mask = restate.slot_mask(d.batch, k)
+    ref = restate.phi_pm(eigV, d.edge_index, mask, sd, "", 2, False)
+    gi = GraphIndex(d.edge_index.to(DEV), d.batch.to(DEV), d.num_graphs)
+    sl = gi.slots_all(pad4(32))
+    idx = slot_row_index(d.batch, k, True)
+    outs = []
+    for sign in (1.0, -1.0):
+        x0 = build_phi_input(gi, sl, (sign * d.eigen_vectors).to(DEV))
+        with torch.no_grad():
+            xr, _ = phi.forward_rows(x0, gi, k, True)
+        outs.append(rows_to_dense(xr[0].cpu(), idx, 32) + rows_to_dense(xr[1].cpu(), idx, 32))
+    assert_close_rel(outs[0], ref, TOL, what="phi eval")
+    # exact sign invariance in eval mode (SURVEY §4 [probe]: max|f(V) - f(-V)| = 0)
+    assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("shape,B,ignore_eigval", [("alchemy", 20, False), ("zinc", 10, True)])
+def test_signnet_rho0_module(shape, B, ignore_eigval):
+    """SignNet with nl_rho = 0 (rho = sum over slots -> Linear -> BN) end to end through forward(data)."""
+    from signnet_basisnet_b200.sign_net import SignNet
+
+    torch.manual_seed(4)
+    d = synth_batch(B, shape, seed=13)
+    net = SignNet(48, 3, nl_rho=0, ignore_eigval=ignore_eigval).to(DEV).train()
+    sd = _cpu_sd(net)
+    eigS, eigV = restate.dense_list_evd(d.eigen_values, d.eigen_vectors, d.batch)
+    ref = restate.sign_net(eigS, eigV, d.edge_index, d.batch, sd, "", 3, 0, ignore_eigval, True)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2))
+    (ref * w).sum().backward()
+    out = net(d.to(DEV))
+    assert out.shape == ref.shape
+    assert_close_rel(out.cpu(), ref.detach(), TOL, what="SignNet(nl_rho=0)")
+    (out * w.to(DEV)).sum().backward()
+    assert_grads_close({n_: p.grad.cpu() for n_, p in net.named_parameters() if p.grad is not None},
+                       {n_: v.grad for n_, v in sd.items() if v.requires_grad and v.grad is not None}, TOL, "signnet")
+    _check_buffers(net, sd, "signnet")
+    # tensor-level overload: forward(x, edge_index, eigvecs[N,k], batch, edge_attr, eigvals[N,k])
+    net2 = SignNet(48, 3, nl_rho=0, ignore_eigval=ignore_eigval).to(DEV).train()
+    net2.load_state_dict({k_: v.detach() for k_, v in _cpu_sd(net, False).items()})
+    net.load_state_dict(net2.state_dict())
+    dd = d.to(DEV)
+    o1 = net(dd)
+    o2 = net2(None, dd.edge_index, eigV.to(DEV), dd.batch, None, eigS.to(DEV))
+    assert torch.equal(o1, o2)

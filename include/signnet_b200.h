@@ -115,18 +115,21 @@ int64_t sb_linear_wgrad_workspace_floats(void);
 int sb_col_stats(const float* x, int64_t ld, int64_t R, int32_t G, int32_t C, double* stats, void* stream);
 int sb_bn_finalize(const double* stats, int64_t M, int32_t G, int32_t C, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, float momentum, float eps, int32_t training, float* a,
-                   float* c, float* mean, float* rstd, void* stream);
+                   float* c, double* mean_rstd /*[2,G,C] fp64 mean and 1/sqrt(var+eps), kept for the backward*/,
+                   void* stream);
 /* out = act(pa*y + pc) + res  (GNN3d tail: norm -> relu -> residual, sign_net.py:40-43) */
 int sb_affine_act_res(const float* y, const float* pa, const float* pc, const float* res, float* out, int64_t ld,
                       int64_t R, int32_t G, int32_t C, int32_t relu, void* stream);
-int sb_bn_bwd_reduce(const float* gout, const float* y, const float* pa, const float* pc, const float* mean,
-                     const float* rstd, float* dz, int64_t ld, int64_t R, int32_t G, int32_t C, int32_t relu,
-                     double* stats, void* stream);
-int sb_bn_bwd_finalize(const double* stats, int64_t M, int32_t G, int32_t C, const float* pa, const float* mean,
-                       const float* rstd, int32_t training, int32_t accumulate, float* dgamma, float* dbeta,
-                       float* al, float* be, float* ga, void* stream);
-int sb_affine2(const float* t1, const float* t2, const float* al, const float* be, const float* ga, float* out,
-               int64_t ld, int64_t R, int32_t G, int32_t C, void* stream);
+/* backward of act(BN(y)): dz = gout*[pa*y+pc > 0]; stats[G,2,C] += (sum dz, sum dz*y_hat) in fp64 */
+int sb_bn_bwd_reduce(const float* gout, const float* y, const float* pa, const float* pc, const double* mean_rstd,
+                     float* dz, int64_t ld, int64_t R, int32_t G, int32_t C, int32_t relu, double* stats,
+                     void* stream);
+/* dgamma/dbeta and the fp64 coefficients coef[3,G,C] of  dY = al*dZ + be*(Y - mean) + ga */
+int sb_bn_bwd_finalize(const double* stats, int64_t M, int32_t G, int32_t C, const float* gamma,
+                       const double* mean_rstd, int32_t training, int32_t accumulate, float* dgamma, float* dbeta,
+                       double* coef, void* stream);
+int sb_affine2(const float* t1, const float* t2, const double* coef, const double* mean_rstd, float* out, int64_t ld,
+               int64_t R, int32_t G, int32_t C, void* stream);
 
 /* sum over eigenvector slots and sign passes -> [N, ldo]  (sign_net.py:113 + :70 ; deepsigns.py:72-81) */
 int sb_slot_sum_fwd(const float* x, int64_t ld, int64_t R, int32_t S, const int64_t* batch, const int32_t* graph_ptr,

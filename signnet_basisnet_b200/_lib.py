@@ -28,11 +28,11 @@ _SIGNATURES = {
     "sb_linear_fwd": "pl" + "pll" + "p" + "pl" + "l" + "iii" + "ipp" + "i" + "p" + "i" + "p",
     "sb_linear_wgrad": "pl" + "pl" + "l" + "iii" + "ipp" + "pll" + "p" + "i" + "p" + "p",
     "sb_col_stats": "pll" + "ii" + "p" + "p",
-    "sb_bn_finalize": "pl" + "ii" + "pppp" + "ff" + "i" + "pppp" + "p",
+    "sb_bn_finalize": "pl" + "ii" + "pppp" + "ff" + "i" + "ppp" + "p",
     "sb_affine_act_res": "ppppp" + "ll" + "iii" + "p",
-    "sb_bn_bwd_reduce": "ppppppp" + "ll" + "iii" + "p" + "p",
-    "sb_bn_bwd_finalize": "pl" + "ii" + "ppp" + "ii" + "ppppp" + "p",
-    "sb_affine2": "pppppp" + "ll" + "ii" + "p",
+    "sb_bn_bwd_reduce": "pppppp" + "ll" + "iii" + "p" + "p",
+    "sb_bn_bwd_finalize": "pl" + "ii" + "pp" + "ii" + "ppp" + "p",
+    "sb_affine2": "ppppp" + "ll" + "ii" + "p",
     "sb_slot_sum_fwd": "pll" + "i" + "ppp" + "l" + "iii" + "pl" + "i" + "p",
     "sb_slot_sum_bwd": "pl" + "pll" + "i" + "ppp" + "l" + "iii" + "i" + "p",
 }

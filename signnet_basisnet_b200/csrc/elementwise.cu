@@ -17,7 +17,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, long long M
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, int training, float* __restrict__ a, float* __restrict__ c,
-                                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                                   double* __restrict__ mean_rstd /*[2,G,C] fp64, for the backward*/) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= C) return;
   const double gm = gamma ? (double)gamma[ch] : 1.0, bt = beta ? (double)beta[ch] : 0.0;
@@ -41,19 +41,21 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, long long M
     const double av = gm * rstd;
     a[(long long)g * C + ch] = (float)av;
     c[(long long)g * C + ch] = (float)(bt - mean * av);
-    if (mean_out) mean_out[(long long)g * C + ch] = (float)mean;
-    if (rstd_out) rstd_out[(long long)g * C + ch] = (float)rstd;
+    if (mean_rstd) {
+      mean_rstd[(long long)g * C + ch] = mean;
+      mean_rstd[((long long)G + g) * C + ch] = rstd;
+    }
   }
 }
 
 extern "C" int sb_bn_finalize(const double* stats, int64_t M, int32_t G, int32_t C, const float* gamma,
                               const float* beta, float* running_mean, float* running_var, float momentum, float eps,
-                              int32_t training, float* a, float* c, float* mean, float* rstd, void* stream) {
+                              int32_t training, float* a, float* c, double* mean_rstd, void* stream) {
   SB_CHECK_ARG(G >= 1 && C >= 1 && a && c, "sb_bn_finalize: bad args");
   SB_CHECK_ARG(training ? (stats != nullptr && M >= 1) : (running_mean && running_var),
                "sb_bn_finalize: training needs stats and M>=1, eval needs running statistics");
   bn_finalize_kernel<<<(unsigned)sb_ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
-      stats, M, G, C, gamma, beta, running_mean, running_var, momentum, eps, training, a, c, mean, rstd);
+      stats, M, G, C, gamma, beta, running_mean, running_var, momentum, eps, training, a, c, mean_rstd);
   SB_CHECK_LAUNCH("sb_bn_finalize");
   return SB_OK;
 }
@@ -68,9 +70,9 @@ __global__ void __launch_bounds__(EW_THREADS) col_stats_kernel(const float* __re
   const int rpi = EW_THREADS / ldv;
   const int g = blockIdx.y;
   const int cg = threadIdx.x % ldv, rs = threadIdx.x / ldv;
-  float s[VEC], q[VEC];
+  double s[VEC], q[VEC];  // fp64 accumulation (B200 runs fp64 adds at half the fp32 rate; the kernel is HBM bound)
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
+  for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.0;
   if (rs < rpi) {
     for (long long r = (long long)blockIdx.x * rpi + rs; r < R; r += (long long)gridDim.x * rpi) {
       const float* p = x + ((long long)g * R + r) * ld + cg * VEC;
@@ -82,15 +84,15 @@ __global__ void __launch_bounds__(EW_THREADS) col_stats_kernel(const float* __re
         v[0] = __ldg(p);
       }
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+      for (int j = 0; j < VEC; ++j) { s[j] += (double)v[j]; q[j] += (double)v[j] * (double)v[j]; }
     }
   }
   const int W = ldv * VEC;
   if (rs < rpi) {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      red[(rs * 2 + 0) * W + cg * VEC + j] = (double)s[j];
-      red[(rs * 2 + 1) * W + cg * VEC + j] = (double)q[j];
+      red[(rs * 2 + 0) * W + cg * VEC + j] = s[j];
+      red[(rs * 2 + 1) * W + cg * VEC + j] = q[j];
     }
   }
   __syncthreads();
@@ -182,26 +184,28 @@ extern "C" int sb_affine_act_res(const float* y, const float* pa, const float* p
 __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const float* gout, const float* __restrict__ y,
                                                                    const float* __restrict__ pa,
                                                                    const float* __restrict__ pc,
-                                                                   const float* __restrict__ mean,
-                                                                   const float* __restrict__ rstd, float* dz,
-                                                                   long long ld, long long R, int C, int relu,
+                                                                   const double* __restrict__ mean_rstd, float* dz,
+                                                                   long long ld, long long R, int G, int C, int relu,
                                                                    double* __restrict__ stats) {
   extern __shared__ double red[];
   const int ldv = (int)(ld >> 2);
   const int rpi = EW_THREADS / ldv;
   const int g = blockIdx.y;
   const int cg = threadIdx.x % ldv, rs = threadIdx.x / ldv;
-  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  // fp64 accumulation: the BatchNorm backward projects out mean and x_hat components, and gradients upstream are
+  // the small residual of that cancellation (amplified by var/eps), so the sums must be far more accurate than fp32.
+  double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
   if (rs < rpi) {
-    float a4[4], c4[4], m4[4], r4[4];
+    float a4[4], c4[4];
+    double m4[4], r4[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int col = cg * 4 + j;
       const bool ok = col < C;
       a4[j] = ok ? __ldg(pa + (long long)g * C + col) : 0.f;
       c4[j] = ok ? __ldg(pc + (long long)g * C + col) : 0.f;
-      m4[j] = ok ? __ldg(mean + (long long)g * C + col) : 0.f;
-      r4[j] = ok ? __ldg(rstd + (long long)g * C + col) : 0.f;
+      m4[j] = ok ? mean_rstd[(long long)g * C + col] : 0.0;
+      r4[j] = ok ? mean_rstd[((long long)G + g) * C + col] : 0.0;
     }
     for (long long r = (long long)blockIdx.x * rpi + rs; r < R; r += (long long)gridDim.x * rpi) {
       const long long off = ((long long)g * R + r) * ld + cg * 4;
@@ -215,8 +219,8 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const float* 
         if (relu && !(fmaf(a4[j], yi[j], c4[j]) > 0.f)) d = 0.f;
         if (cg * 4 + j >= C) d = 0.f;
         o[j] = d;
-        s1[j] += d;
-        s2[j] = fmaf(d, (yi[j] - m4[j]) * r4[j], s2[j]);
+        s1[j] += (double)d;
+        s2[j] += (double)d * (((double)yi[j] - m4[j]) * r4[j]);
       }
       if (dz) *reinterpret_cast<float4*>(dz + off) = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -225,8 +229,8 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const float* 
   if (rs < rpi) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      red[(rs * 2 + 0) * W + cg * 4 + j] = (double)s1[j];
-      red[(rs * 2 + 1) * W + cg * 4 + j] = (double)s2[j];
+      red[(rs * 2 + 0) * W + cg * 4 + j] = s1[j];
+      red[(rs * 2 + 1) * W + cg * 4 + j] = s2[j];
     }
   }
   __syncthreads();
@@ -241,10 +245,10 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const float* 
 }
 
 extern "C" int sb_bn_bwd_reduce(const float* gout, const float* y, const float* pa, const float* pc,
-                                const float* mean, const float* rstd, float* dz, int64_t ld, int64_t R, int32_t G,
-                                int32_t C, int32_t relu, double* stats, void* stream) {
+                                const double* mean_rstd, float* dz, int64_t ld, int64_t R, int32_t G, int32_t C,
+                                int32_t relu, double* stats, void* stream) {
   SB_CHECK_ARG(ld % 4 == 0 && ld >= C && ld / 4 <= EW_THREADS && G >= 1, "sb_bn_bwd_reduce: bad leading dim");
-  SB_CHECK_ARG(gout && y && pa && pc && mean && rstd && stats, "sb_bn_bwd_reduce: null argument");
+  SB_CHECK_ARG(gout && y && pa && pc && mean_rstd && stats, "sb_bn_bwd_reduce: null argument");
   if (R == 0) return SB_OK;
   const int ldv = (int)(ld / 4);
   const int rpi = EW_THREADS / ldv;
@@ -254,61 +258,65 @@ extern "C" int sb_bn_bwd_reduce(const float* gout, const float* y, const float* 
   if (blocks < 1) blocks = 1;
   dim3 grid((unsigned)blocks, (unsigned)G);
   const size_t smem = (size_t)rpi * 2 * ldv * 4 * sizeof(double);
-  bn_bwd_reduce_kernel<<<grid, EW_THREADS, smem, (cudaStream_t)stream>>>(gout, y, pa, pc, mean, rstd, dz, ld, R, C,
+  bn_bwd_reduce_kernel<<<grid, EW_THREADS, smem, (cudaStream_t)stream>>>(gout, y, pa, pc, mean_rstd, dz, ld, R, G, C,
                                                                         relu, stats);
   SB_CHECK_LAUNCH("sb_bn_bwd_reduce");
   return SB_OK;
 }
 
-// dgamma (+)= sum_g s2[g], dbeta (+)= sum_g s1[g]; coefficient vectors of  dY = al*dZ + be*Y + ga :
-//   training:  al = a, be = -a*rstd*m2, ga = -a*m1 + a*rstd*m2*mean      (m1 = s1/M, m2 = s2/M)
-//   eval:      al = a, be = 0,          ga = 0
+// dgamma (+)= sum_g s2[g], dbeta (+)= sum_g s1[g]; fp64 coefficients of the centred form
+//     dY = al * dZ + be * (Y - mean) + ga
+//   training:  al = a, be = -a * rstd^2 * m2, ga = -a * m1        (a = gamma * rstd, m1 = s1/M, m2 = s2/M)
+//   eval:      al = a, be = 0,                ga = 0
+// Centred + fp64 on purpose: the upstream weight gradient is the eps/(var+eps)-sized residual of
+// sum dY * Y, so a coefficient rounded to fp32 (relative 6e-8) shows up amplified by var/eps (and by mean^2/eps in the
+// uncentred form) in dW of the preceding Linear.
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, long long M, int G, int C,
-                                       const float* __restrict__ pa, const float* __restrict__ mean,
-                                       const float* __restrict__ rstd, int training, int accumulate,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ al,
-                                       float* __restrict__ be, float* __restrict__ ga) {
+                                       const float* __restrict__ gamma, const double* __restrict__ mean_rstd,
+                                       int training, int accumulate, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, double* __restrict__ coef /*[3,G,C]*/) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= C) return;
   double dg = 0.0, db = 0.0;
+  const double gm = gamma ? (double)gamma[ch] : 1.0;
   for (int g = 0; g < G; ++g) {
     const double s1 = stats[((long long)g * 2 + 0) * C + ch], s2 = stats[((long long)g * 2 + 1) * C + ch];
     dg += s2;
     db += s1;
-    const double a = (double)pa[(long long)g * C + ch];
+    const double rs = mean_rstd[((long long)G + g) * C + ch];
+    const double a = gm * rs;
     double bev = 0.0, gav = 0.0;
     if (training) {
       const double m1 = s1 / (double)M, m2 = s2 / (double)M;
-      const double rs = (double)rstd[(long long)g * C + ch], mu = (double)mean[(long long)g * C + ch];
       bev = -a * rs * m2;
-      gav = -a * m1 + a * rs * m2 * mu;
+      gav = -a * m1;
     }
-    al[(long long)g * C + ch] = (float)a;
-    be[(long long)g * C + ch] = (float)bev;
-    ga[(long long)g * C + ch] = (float)gav;
+    coef[((long long)0 * G + g) * C + ch] = a;
+    coef[((long long)1 * G + g) * C + ch] = bev;
+    coef[((long long)2 * G + g) * C + ch] = gav;
   }
   if (dgamma) dgamma[ch] = accumulate ? dgamma[ch] + (float)dg : (float)dg;
   if (dbeta) dbeta[ch] = accumulate ? dbeta[ch] + (float)db : (float)db;
 }
 
-extern "C" int sb_bn_bwd_finalize(const double* stats, int64_t M, int32_t G, int32_t C, const float* pa,
-                                  const float* mean, const float* rstd, int32_t training, int32_t accumulate,
-                                  float* dgamma, float* dbeta, float* al, float* be, float* ga, void* stream) {
-  SB_CHECK_ARG(stats && pa && mean && rstd && al && be && ga && M >= 1, "sb_bn_bwd_finalize: null argument");
+extern "C" int sb_bn_bwd_finalize(const double* stats, int64_t M, int32_t G, int32_t C, const float* gamma,
+                                  const double* mean_rstd, int32_t training, int32_t accumulate, float* dgamma,
+                                  float* dbeta, double* coef, void* stream) {
+  SB_CHECK_ARG(stats && mean_rstd && coef && M >= 1, "sb_bn_bwd_finalize: null argument");
   bn_bwd_finalize_kernel<<<(unsigned)sb_ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
-      stats, M, G, C, pa, mean, rstd, training, accumulate, dgamma, dbeta, al, be, ga);
+      stats, M, G, C, gamma, mean_rstd, training, accumulate, dgamma, dbeta, coef);
   SB_CHECK_LAUNCH("sb_bn_bwd_finalize");
   return SB_OK;
 }
 
-// out = al[g,c]*t1 + be[g,c]*t2 + ga[g,c]   (out may alias t1; pad columns -> 0)
+// out = al[g,c]*t1 + be[g,c]*(t2 - mean[g,c]) + ga[g,c]  evaluated in fp64, rounded once (out may alias t1)
 __global__ void __launch_bounds__(EW_THREADS) affine2_kernel(const float* t1, const float* __restrict__ t2,
-                                                             const float* __restrict__ al,
-                                                             const float* __restrict__ be,
-                                                             const float* __restrict__ ga, float* out, long long ld,
-                                                             long long R, int G, int C) {
+                                                             const double* __restrict__ coef,
+                                                             const double* __restrict__ mean_rstd, float* out,
+                                                             long long ld, long long R, int G, int C) {
   const long long ld4 = ld >> 2;
   const long long total = (long long)G * R * ld4;
+  const long long GC = (long long)G * C;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     const long long row = t / ld4;
@@ -323,7 +331,7 @@ __global__ void __launch_bounds__(EW_THREADS) affine2_kernel(const float* t1, co
       const int col = c4 * 4 + j;
       if (col < C) {
         const long long p = (long long)g * C + col;
-        o[j] = fmaf(__ldg(al + p), ui[j], fmaf(__ldg(be + p), vi[j], __ldg(ga + p)));
+        o[j] = (float)(coef[p] * (double)ui[j] + coef[GC + p] * ((double)vi[j] - mean_rstd[p]) + coef[2 * GC + p]);
       } else {
         o[j] = 0.f;
       }
@@ -332,8 +340,8 @@ __global__ void __launch_bounds__(EW_THREADS) affine2_kernel(const float* t1, co
   }
 }
 
-extern "C" int sb_affine2(const float* t1, const float* t2, const float* al, const float* be, const float* ga,
-                          float* out, int64_t ld, int64_t R, int32_t G, int32_t C, void* stream) {
+extern "C" int sb_affine2(const float* t1, const float* t2, const double* coef, const double* mean_rstd, float* out,
+                          int64_t ld, int64_t R, int32_t G, int32_t C, void* stream) {
   SB_CHECK_ARG(ld % 4 == 0 && ld >= C && G >= 1, "sb_affine2: ld must be a multiple of 4 and >= C");
   if (R == 0) return SB_OK;
   const long long total = (long long)G * R * (ld / 4);
@@ -341,7 +349,7 @@ extern "C" int sb_affine2(const float* t1, const float* t2, const float* al, con
   const long long cap = (long long)sb_num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  affine2_kernel<<<(unsigned)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>(t1, t2, al, be, ga, out, ld, R, G, C);
+  affine2_kernel<<<(unsigned)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>(t1, t2, coef, mean_rstd, out, ld, R, G, C);
   SB_CHECK_LAUNCH("sb_affine2");
   return SB_OK;
 }

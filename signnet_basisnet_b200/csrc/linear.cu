@@ -174,9 +174,9 @@ __global__ void __launch_bounds__(LIN_THREADS, (BN == 64) ? 2 : 1) linear_fwd_ke
       const long long row0 = (tile - (long long)g * tpg) * LIN_BM;
       const int rows = (int)((a.R - row0 < LIN_BM) ? (a.R - row0) : LIN_BM);
       const long long base = (long long)g * a.R + row0;
-      float ssum[NT], ssq[NT];
+      double ssum[NT], ssq[NT];
 #pragma unroll
-      for (int j = 0; j < NT; ++j) ssum[j] = 0.f, ssq[j] = 0.f;
+      for (int j = 0; j < NT; ++j) ssum[j] = 0.0, ssq[j] = 0.0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = ty + 16 * i;
@@ -194,8 +194,10 @@ __global__ void __launch_bounds__(LIN_THREADS, (BN == 64) ? 2 : 1) linear_fwd_ke
                 if (a.bias) t += __ldg(a.bias + col);
                 if (a.accumulate) t += yrow[col];
                 if (a.relu) t = fmaxf(t, 0.f);
-                ssum[v * 4 + j] += t;
-                ssq[v * 4 + j] = fmaf(t, t, ssq[v * 4 + j]);
+                if (a.stats) {
+                  ssum[v * 4 + j] += (double)t;
+                  ssq[v * 4 + j] += (double)t * (double)t;
+                }
               } else {
                 t = 0.f;
               }
@@ -226,8 +228,8 @@ __global__ void __launch_bounds__(LIN_THREADS, (BN == 64) ? 2 : 1) linear_fwd_ke
             for (int j = 0; j < 4; ++j) {
               const int col = v * 64 + tx * 4 + j;
               if (col < N) {
-                atomicAdd(&sacc[(g * 2 + 0) * BN + col], (double)ssum[v * 4 + j]);
-                atomicAdd(&sacc[(g * 2 + 1) * BN + col], (double)ssq[v * 4 + j]);
+                atomicAdd(&sacc[(g * 2 + 0) * BN + col], ssum[v * 4 + j]);
+                atomicAdd(&sacc[(g * 2 + 1) * BN + col], ssq[v * 4 + j]);
               }
             }
         }

@@ -43,24 +43,25 @@ def linear_wgrad(gy, ldg, x, ldx, R, G, N, K, dW, rs, cs, db=None, pro=0, pa=Non
 
 
 def bn_finalize(stats, M, G, C, gamma, beta, rmean, rvar, training, device):
-    """-> (a, c, mean, rstd) each [G, C]; updates the running buffers in place when training."""
-    out = torch.empty(4, G, C, dtype=torch.float32, device=device)
+    """-> (a, c) fp32 [G, C] with BN(x) = a*x + c, and mean_rstd fp64 [2, G, C] for the backward; updates the running
+    buffers in place when training."""
+    out = torch.empty(2, G, C, dtype=torch.float32, device=device)
+    mr = torch.empty(2, G, C, dtype=torch.float64, device=device)
     _call("sb_bn_finalize", _p(stats), M, G, C, _p(gamma), _p(beta), _p(rmean), _p(rvar), BN_MOMENTUM, BN_EPS,
-          int(training), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]))
-    return out[0], out[1], out[2], out[3]
+          int(training), _p(out[0]), _p(out[1]), _p(mr))
+    return out[0], out[1], mr
 
 
-def bn_backward(gout, y, a, c, mean, rstd, ld, R, G, C, relu, training, dz_out):
+def bn_backward(gout, y, a, c, mr, gamma, ld, R, G, C, relu, training, dz_out):
     """dz_out <- gradient w.r.t. the BatchNorm input y, given gout = dL/d act(BN(y)).  Returns (dgamma, dbeta)."""
     dev = y.device
     stats = torch.zeros(G, 2, C, dtype=torch.float64, device=dev)
-    _call("sb_bn_bwd_reduce", _p(gout), _p(y), _p(a), _p(c), _p(mean), _p(rstd), _p(dz_out), ld, R, G, C, int(relu),
-          _p(stats))
-    coef = torch.empty(3, G, C, dtype=torch.float32, device=dev)
+    _call("sb_bn_bwd_reduce", _p(gout), _p(y), _p(a), _p(c), _p(mr), _p(dz_out), ld, R, G, C, int(relu), _p(stats))
+    coef = torch.empty(3, G, C, dtype=torch.float64, device=dev)
     dgb = torch.empty(2, C, dtype=torch.float32, device=dev)
-    _call("sb_bn_bwd_finalize", _p(stats), R, G, C, _p(a), _p(mean), _p(rstd), int(training), 0, _p(dgb[0]),
-          _p(dgb[1]), _p(coef[0]), _p(coef[1]), _p(coef[2]))
-    _call("sb_affine2", _p(dz_out), _p(y), _p(coef[0]), _p(coef[1]), _p(coef[2]), _p(dz_out), ld, R, G, C)
+    _call("sb_bn_bwd_finalize", _p(stats), R, G, C, _p(gamma), _p(mr), int(training), 0, _p(dgb[0]), _p(dgb[1]),
+          _p(coef))
+    _call("sb_affine2", _p(dz_out), _p(y), _p(coef), _p(mr), _p(dz_out), ld, R, G, C)
     return dgb[0], dgb[1]
 
 
@@ -118,21 +119,21 @@ class BatchNormActFn(torch.autograd.Function):
         if training:
             stats = torch.zeros(1, 2, C, dtype=torch.float64, device=dev)
             _call("sb_col_stats", _p(x), ld, M, 1, C, _p(stats))
-        a, c, mean, rstd = bn_finalize(stats, M, 1, C, gamma, beta, rmean, rvar, training, dev)
+        a, c, mr = bn_finalize(stats, M, 1, C, gamma, beta, rmean, rvar, training, dev)
         out = torch.empty_like(x)
         _call("sb_affine_act_res", _p(x), _p(a), _p(c), _p(res), _p(out), ld, M, 1, C, int(relu))
-        ctx.save_for_backward(x, a, c, mean, rstd)
+        ctx.save_for_backward(x, a, c, mr, gamma)
         ctx.cfg = (training, relu, C, res is not None)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        x, a, c, mean, rstd = ctx.saved_tensors
+        x, a, c, mr, gamma = ctx.saved_tensors
         training, relu, C, has_res = ctx.cfg
         gout = gout.contiguous()
         M, ld = x.shape
         gx = torch.empty_like(x)
-        dgamma, dbeta = bn_backward(gout, x, a, c, mean, rstd, ld, M, 1, C, relu, training, gx)
+        dgamma, dbeta = bn_backward(gout, x, a, c, mr, gamma, ld, M, 1, C, relu, training, gx)
         return gx, dgamma, dbeta, (gout if has_res else None), None, None, None, None, None
 
 

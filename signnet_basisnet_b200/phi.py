@@ -59,15 +59,17 @@ class PhiStackFn(torch.autograd.Function):
             st0 = torch.zeros(S, 2, h, dtype=torch.float64, device=dev) if training else None
             H = torch.empty(S, R, ldh, dtype=torch.float32, device=dev)
             linear_fwd(A, ld_in, W0, d_in, 1, None, H, ldh, R, S, d_in, h, stats=st0)
-            a0, c0, m0, r0 = bn_finalize(st0, R, S, h, g0, b0, rm0, rv0, training, dev)
+            a0, c0, mr0 = bn_finalize(st0, R, S, h, g0, b0, rm0, rv0, training, dev)
             st1 = torch.zeros(S, 2, d, dtype=torch.float64, device=dev) if training else None
             Y = torch.empty(S, R, ldd, dtype=torch.float32, device=dev)
             linear_fwd(H, ldh, W1, h, 1, b1, Y, ldd, R, S, h, d, pro=2, pa=a0, pc=c0, stats=st1)
-            a1, c1, m1, r1 = bn_finalize(st1, R, S, d, g1, bb1, rm1, rv1, training, dev)
+            a1, c1, mr1 = bn_finalize(st1, R, S, d, g1, bb1, rm1, rv1, training, dev)
             Xn = torch.empty(S, R, ldd, dtype=torch.float32, device=dev)
             _call("sb_affine_act_res", _p(Y), _p(a1), _p(c1), _p(X if l > 0 else None), _p(Xn), ldd, R, S, d, 1)
             saved += [X, A, H, Y]
-            vecs += [a0, c0, m0, r0, a1, c1, m1, r1]
+            vecs += [a0, c0, mr0, a1, c1, mr1]
+            if cfg.get("capture") is not None:  # test hook: pre-activations + BN affines (activation patterns)
+                cfg["capture"].append(dict(H=H, a0=a0, c0=c0, Y=Y, a1=a1, c1=c1, h=h, d=d))
             X, ld_in = Xn, ldd
         ctx.cfg = cfg
         ctx.n_params = len(params)
@@ -81,8 +83,8 @@ class PhiStackFn(torch.autograd.Function):
         slots, training, dims = cfg["slots"], cfg["training"], cfg["dims"]
         L = len(dims)
         tensors = list(ctx.saved_tensors)
-        saved, vecs = tensors[:4 * L], tensors[4 * L:12 * L]
-        it = iter(tensors[12 * L:])
+        saved, vecs = tensors[:4 * L], tensors[4 * L:10 * L]
+        it = iter(tensors[10 * L:])
         params = [None if none else next(it) for none in ctx.param_none]
         S, R = gout.shape[0], slots.R
         dev = gout.device
@@ -91,14 +93,14 @@ class PhiStackFn(torch.autograd.Function):
         for l in reversed(range(L)):
             d_in, h, d = dims[l]
             X, A, H, Y = saved[4 * l:4 * l + 4]
-            a0, c0, m0, r0, a1, c1, m1, r1 = vecs[8 * l:8 * l + 8]
+            a0, c0, mr0, a1, c1, mr1 = vecs[6 * l:6 * l + 6]
             W0, g0, b0, W1, b1, eps, g1, bb1 = params[l * PARAMS_PER_LAYER:(l + 1) * PARAMS_PER_LAYER]
             ld_in = 1 if X.dim() == 2 else X.shape[2]
             ldh, ldd = pad4(h), pad4(d)
             base = l * PARAMS_PER_LAYER
             # outer BN + ReLU:  dY
             dY = torch.empty(S, R, ldd, dtype=torch.float32, device=dev)
-            grads[base + 6], grads[base + 7] = bn_backward(G, Y, a1, c1, m1, r1, ldd, R, S, d, True, training, dY)
+            grads[base + 6], grads[base + 7] = bn_backward(G, Y, a1, c1, mr1, g1, ldd, R, S, d, True, training, dY)
             # second Linear: dW1, db1 (input recomputed as relu(bn0(H)) in the prologue), dP
             gW1 = torch.empty_like(W1)
             gb1 = torch.empty_like(b1) if b1 is not None else None
@@ -108,7 +110,7 @@ class PhiStackFn(torch.autograd.Function):
             linear_fwd(dY, ldd, W1, 1, h, None, dH, ldh, R, S, d, h)
             del dY
             # inner BN + ReLU:  dH (in place)
-            grads[base + 1], grads[base + 2] = bn_backward(dH, H, a0, c0, m0, r0, ldh, R, S, h, True, training, dH)
+            grads[base + 1], grads[base + 2] = bn_backward(dH, H, a0, c0, mr0, g0, ldh, R, S, h, True, training, dH)
             # first Linear: dW0, dA
             gW0 = torch.empty_like(W0)
             linear_wgrad(dH, ldh, A, ld_in, R, S, h, d_in, gW0, d_in, 1, None)

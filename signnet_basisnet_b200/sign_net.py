@@ -144,7 +144,7 @@ class GNN3d(nn.Module):
             buffers.append((bn0.running_mean, bn0.running_var, norm.bn.running_mean, norm.bn.running_var))
         return dims, params, buffers
 
-    def forward_rows(self, x0, gi: GraphIndex, k: int, masked: bool = True):
+    def forward_rows(self, x0, gi: GraphIndex, k: int, masked: bool = True, capture=None):
         """x0 [2, R] (+v, -v in slot-row order) -> X_L [2, R, pad4(n_out)]."""
         dims, params, buffers = self._flat_params()
         d = dims[-1][2]
@@ -154,7 +154,8 @@ class GNN3d(nn.Module):
             for conv, norm in zip(self.convs, self.norms):
                 conv.nn.norms[0].bn.num_batches_tracked += 2
                 norm.bn.num_batches_tracked += 2
-        cfg = dict(slots=slots, slots_in=slots_in, dims=dims, training=self.training, buffers=buffers)
+        cfg = dict(slots=slots, slots_in=slots_in, dims=dims, training=self.training, buffers=buffers,
+                   capture=capture)
         return PhiStackFn.apply(x0, cfg, *params), slots
 
     def forward(self, x, edge_index, edge_attr=None, mask=None, batch=None, num_graphs=None):

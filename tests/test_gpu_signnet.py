@@ -5,7 +5,8 @@ import pytest
 import torch
 
 import restate
-from helpers import assert_close_rel, assert_grads_close, rows_to_dense, slot_row_index
+from helpers import (assert_close_rel, assert_grads_parity, assert_parity, dense_to_rows, rows_to_dense,
+                     slot_row_index)
 from signnet_basisnet_b200.synth import synth_batch
 
 pytestmark = pytest.mark.gpu
@@ -13,8 +14,9 @@ DEV = "cuda"
 TOL = 1e-5
 
 
-def _cpu_sd(module, leaf=True):
-    sd = {k: v.detach().cpu().clone() for k, v in module.state_dict().items()}
+def _cpu_sd(module, leaf=True, dtype=torch.float32):
+    sd = {k: (v.detach().cpu().clone().to(dtype) if v.is_floating_point() else v.detach().cpu().clone())
+          for k, v in module.state_dict().items()}
     if leaf:
         for k, v in sd.items():
             if v.is_floating_point() and "running_" not in k:
@@ -22,12 +24,16 @@ def _cpu_sd(module, leaf=True):
     return sd
 
 
-def _check_buffers(module, sd, what):
+def _check_buffers(module, sd, sd64, what):
     for name, buf in module.named_buffers():
         if buf.is_floating_point():
-            assert_close_rel(buf.cpu(), sd[name], TOL, what=f"{what} buffer {name}")
+            assert_parity(buf, sd[name], sd64[name], TOL, what=f"{what} buffer {name}")
         else:
             assert torch.equal(buf.cpu(), sd[name]), f"{what} buffer {name}: {buf} vs {sd[name]}"
+
+
+def _grads(sd):
+    return {n_: v.grad for n_, v in sd.items() if v.requires_grad and v.grad is not None}
 
 
 @pytest.mark.parametrize("shape,B,flavour,nhid,nl", [("alchemy", 24, "alchemy", 64, 3), ("zinc", 16, "alchemy", 128, 2),
@@ -45,28 +51,57 @@ def test_phi_stack_forward_backward(shape, B, flavour, nhid, nl):
                 p.uniform_(0.5, 1.5)
             elif n_.endswith("bn.bias") or n_.endswith("eps"):
                 p.uniform_(-0.3, 0.3)
-    sd = _cpu_sd(phi)
     _, eigV = restate.dense_list_evd(d.eigen_values, d.eigen_vectors, d.batch)
     k = eigV.shape[1]
     mask = restate.slot_mask(d.batch, k)
-    ref = restate.phi_pm(eigV, d.edge_index, mask, sd, "", nl, True)
-    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1)) * mask.unsqueeze(-1)
-    (ref * w).sum().backward()
+    w = torch.randn(eigV.shape[0], k, nhid, generator=torch.Generator().manual_seed(1)) * mask.unsqueeze(-1)
+    sd, sd64 = _cpu_sd(phi), _cpu_sd(phi, dtype=torch.float64)
 
     gi = GraphIndex(d.edge_index.to(DEV), d.batch.to(DEV), d.num_graphs)
     sl = gi.slots_all(pad4(nhid))
     assert sl.k == k
     x0 = build_phi_input(gi, sl, d.eigen_vectors.to(DEV))
-    xr, sl = phi.forward_rows(x0, gi, k, True)
+    cap = []
+    xr, sl = phi.forward_rows(x0, gi, k, True, capture=cap)
     idx = slot_row_index(d.batch, k, True)
+
+    # Activation patterns of the CUDA pass, imposed on the oracle (see restate.ACTIVATION_OVERRIDE): pattern[tag] is
+    # the [k, N, C] 0/1 mask of one ReLU.  They must agree with the oracle's own pattern except where the exact (fp64)
+    # pre-activation is within rounding distance of zero.
+    pattern, n_flip = {}, [0]
+    for l, c_ in enumerate(cap):
+        for key, a_, c0_, C, tag in ((c_["H"], c_["a0"], c_["c0"], c_["h"], f"convs.{l}.nn.norms.0"),
+                                     (c_["Y"], c_["a1"], c_["c1"], c_["d"], f"norms.{l}")):
+            z = torch.addcmul(c0_[:, None, :], a_[:, None, :], key[..., :C])
+            for s_, sign in enumerate("+-"):
+                pattern[sign + tag] = rows_to_dense((z[s_] > 0).float().cpu(), idx, C).transpose(0, 1)
+
+    def act(dtype):
+        def f(z, tag):
+            m = pattern[tag].to(dtype)
+            flips = ((z > 0).to(dtype) != m) & mask.transpose(0, 1).unsqueeze(-1)
+            if flips.any():
+                n_flip[0] += int(flips.sum())
+                assert float(z.detach()[flips].abs().max()) <= 1e-5 * float(z.detach().abs().max()), f"activation pattern differs at {tag}"
+            return z * m
+        return f
+
+    try:
+        restate.ACTIVATION_OVERRIDE = act(torch.float32)
+        ref = restate.phi_pm(eigV, d.edge_index, mask, sd, "", nl, True)
+        (ref * w).sum().backward()
+        restate.ACTIVATION_OVERRIDE = act(torch.float64)
+        ref64 = restate.phi_pm(eigV.double(), d.edge_index, mask, sd64, "", nl, True)
+        (ref64 * w.double()).sum().backward()
+    finally:
+        restate.ACTIVATION_OVERRIDE = None
     got = rows_to_dense(xr[0].cpu(), idx, nhid) + rows_to_dense(xr[1].cpu(), idx, nhid)
-    assert_close_rel(got, ref.detach(), TOL, what="phi(+v)+phi(-v)")
-    from helpers import dense_to_rows
+    assert_parity(got, ref, ref64, TOL, what="phi(+v)+phi(-v)")
     w_rows = dense_to_rows(w, idx, pad4(nhid)).to(DEV)
     (xr * w_rows.unsqueeze(0)).sum().backward()
-    assert_grads_close({n_: p.grad.cpu() for n_, p in phi.named_parameters() if p.grad is not None},
-                       {n_: v.grad for n_, v in sd.items() if v.requires_grad and v.grad is not None}, TOL, "phi")
-    _check_buffers(phi, sd, "phi")
+    assert_grads_parity({n_: p.grad.cpu() for n_, p in phi.named_parameters() if p.grad is not None},
+                        _grads(sd), _grads(sd64), TOL, "phi")
+    _check_buffers(phi, sd, sd64, "phi")
 
 
 def test_phi_eval_mode_and_sign_invariance():
@@ -110,18 +145,20 @@ def test_signnet_rho0_module(shape, B, ignore_eigval):
     torch.manual_seed(4)
     d = synth_batch(B, shape, seed=13)
     net = SignNet(48, 3, nl_rho=0, ignore_eigval=ignore_eigval).to(DEV).train()
-    sd = _cpu_sd(net)
+    sd, sd64 = _cpu_sd(net), _cpu_sd(net, dtype=torch.float64)
     eigS, eigV = restate.dense_list_evd(d.eigen_values, d.eigen_vectors, d.batch)
     ref = restate.sign_net(eigS, eigV, d.edge_index, d.batch, sd, "", 3, 0, ignore_eigval, True)
     w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2))
     (ref * w).sum().backward()
+    ref64 = restate.sign_net(eigS.double(), eigV.double(), d.edge_index, d.batch, sd64, "", 3, 0, ignore_eigval, True)
+    (ref64 * w.double()).sum().backward()
     out = net(d.to(DEV))
     assert out.shape == ref.shape
-    assert_close_rel(out.cpu(), ref.detach(), TOL, what="SignNet(nl_rho=0)")
+    assert_parity(out, ref, ref64, TOL, what="SignNet(nl_rho=0)")
     (out * w.to(DEV)).sum().backward()
-    assert_grads_close({n_: p.grad.cpu() for n_, p in net.named_parameters() if p.grad is not None},
-                       {n_: v.grad for n_, v in sd.items() if v.requires_grad and v.grad is not None}, TOL, "signnet")
-    _check_buffers(net, sd, "signnet")
+    assert_grads_parity({n_: p.grad.cpu() for n_, p in net.named_parameters() if p.grad is not None},
+                        _grads(sd), _grads(sd64), TOL, "signnet")
+    _check_buffers(net, sd, sd64, "signnet")
     # tensor-level overload: forward(x, edge_index, eigvecs[N,k], batch, edge_attr, eigvals[N,k])
     net2 = SignNet(48, 3, nl_rho=0, ignore_eigval=ignore_eigval).to(DEV).train()
     net2.load_state_dict({k_: v.detach() for k_, v in _cpu_sd(net, False).items()})

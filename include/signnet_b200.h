@@ -139,6 +139,26 @@ int sb_slot_sum_bwd(const float* gout, int64_t ldo, float* gx, int64_t ld, int64
                     const int64_t* batch, const int32_t* graph_ptr, const int64_t* row_ptr, int64_t N, int32_t k,
                     int32_t masked, int32_t limit_by_n, int32_t C, void* stream);
 
+/* ---- K5/K6: GINE predictor pieces on [N, ld] node rows ---------------------------------------------------------------
+ * out_i = (1+eps) x_i + sum_{(j->i)} relu(x_j + e_ji), e [E, ld] indexed by edge id.  Replaces gnn.GINEConv
+ * (Alchemy/sign_net/model_utils/pyg_gnn_wrapper.py:19-28).  Backward: dx (by source, CSC), de per edge, deps. */
+int sb_gine_agg_fwd(const float* x, const float* e, const float* eps, const int32_t* in_ptr, const int32_t* in_src,
+                    const int32_t* in_eid, int64_t N, int32_t ld, float* out, void* stream);
+int sb_gine_agg_bwd(const float* dA, const float* x, const float* e, const float* eps, const int64_t* edge_index,
+                    const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_eid, int64_t N, int64_t E,
+                    int32_t ld, float* dx, float* de, double* deps, void* stream);
+/* graph read-out: scatter(x, batch, reduce='add'|'mean') (model.py:58-61) on the sorted batch */
+int sb_segment_pool_fwd(const float* x, int64_t ldx, const int32_t* graph_ptr, int32_t B, int32_t C, int32_t mean,
+                        float* out, int64_t ldo, void* stream);
+int sb_segment_pool_bwd(const float* gout, int64_t ldo, const int64_t* batch, const int32_t* graph_ptr, int64_t N,
+                        int32_t C, int32_t mean, float* gx, int64_t ldx, void* stream);
+/* DiscreteEncoder (elements.py:21-37), one integer feature column per call; flags bit 0 = index out of range */
+int sb_embedding_fwd(const int64_t* idx, int64_t stride, const float* table, int32_t V, int32_t C, int64_t M,
+                     float* out, int64_t ldo, int32_t accumulate, int32_t* flags, void* stream);
+int sb_embedding_bwd(const int64_t* idx, int64_t stride, const float* g, int64_t ldg, int32_t V, int32_t C, int64_t M,
+                     float* dtable, float* workspace, void* stream);
+int64_t sb_embedding_bwd_workspace_floats(int32_t V, int32_t C);
+
 #ifdef __cplusplus
 }
 #endif

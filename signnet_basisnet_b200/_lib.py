@@ -33,6 +33,12 @@ _SIGNATURES = {
     "sb_bn_bwd_reduce": "pppppp" + "ll" + "iii" + "p" + "p",
     "sb_bn_bwd_finalize": "pl" + "ii" + "pp" + "ii" + "ppp" + "p",
     "sb_affine2": "ppppp" + "ll" + "ii" + "p",
+    "sb_gine_agg_fwd": "pppppp" + "li" + "p" + "p",
+    "sb_gine_agg_bwd": "pppp" + "pppp" + "lli" + "ppp" + "p",
+    "sb_segment_pool_fwd": "plp" + "iii" + "pl" + "p",
+    "sb_segment_pool_bwd": "plpp" + "lii" + "pl" + "p",
+    "sb_embedding_fwd": "plp" + "iil" + "pl" + "ip" + "p",
+    "sb_embedding_bwd": "plpl" + "iil" + "pp" + "p",
     "sb_slot_sum_fwd": "pll" + "i" + "ppp" + "l" + "iii" + "pl" + "i" + "p",
     "sb_slot_sum_bwd": "pl" + "pll" + "i" + "ppp" + "l" + "iii" + "i" + "p",
 }
@@ -59,6 +65,8 @@ def lib():
         L.sb_gin_agg_tile_rows.restype = ctypes.c_int
         L.sb_gin_agg_tile_rows.argtypes = [ctypes.c_int32]
         L.sb_linear_wgrad_workspace_floats.restype = ctypes.c_int64
+        L.sb_embedding_bwd_workspace_floats.restype = ctypes.c_int64
+        L.sb_embedding_bwd_workspace_floats.argtypes = [ctypes.c_int32, ctypes.c_int32]
         for name, sig in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = ctypes.c_int
@@ -69,7 +77,7 @@ def lib():
 
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["sb_last_error", "sb_abi_version", "sb_device_sm_count", "sb_gin_agg_tile_rows",
-                                       "sb_linear_wgrad_workspace_floats"])
+                                       "sb_linear_wgrad_workspace_floats", "sb_embedding_bwd_workspace_floats"])
 
 
 def ptr(t):

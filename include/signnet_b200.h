@@ -131,6 +131,8 @@ int sb_bn_bwd_finalize(const double* stats, int64_t M, int32_t G, int32_t C, con
 int sb_affine2(const float* t1, const float* t2, const double* coef, const double* mean_rstd, float* out, int64_t ld,
                int64_t R, int32_t G, int32_t C, void* stream);
 
+int sb_relu_bwd(const float* g, const float* y, float* out, int64_t n, void* stream); /* out = g * [y > 0] */
+
 /* sum over eigenvector slots and sign passes -> [N, ldo]  (sign_net.py:113 + :70 ; deepsigns.py:72-81) */
 int sb_slot_sum_fwd(const float* x, int64_t ld, int64_t R, int32_t S, const int64_t* batch, const int32_t* graph_ptr,
                     const int64_t* row_ptr, int64_t N, int32_t k, int32_t masked, int32_t limit_by_n, float* out,
@@ -158,6 +160,26 @@ int sb_embedding_fwd(const int64_t* idx, int64_t stride, const float* table, int
 int sb_embedding_bwd(const int64_t* idx, int64_t stride, const float* g, int64_t ldg, int32_t V, int32_t C, int64_t M,
                      float* dtable, float* workspace, void* stream);
 int64_t sb_embedding_bwd_workspace_floats(int32_t V, int32_t C);
+
+/* ---- K7: rho = SetTransformer pieces (Alchemy/sign_net/model_utils/transformer_module.py:44-102) -------------------
+ * Self-attention of every node over its k_b valid eigenvector slots (tokens = slot rows of the node), n_head heads of
+ * width dk packed in columns [h*dk, (h+1)*dk) of q/k/v/o [R, ld].  scores = (q / temperature) k^T, softmax over the
+ * valid keys (== the reference's -1e10 fill + mask), optional attention dropout (counter-based, regenerated in the
+ * backward from `seed`), o = P v. */
+int sb_attention_fwd(const float* q, const float* k, const float* v, int64_t ld, const int64_t* batch,
+                     const int32_t* graph_ptr, const int64_t* row_ptr, int64_t N, int32_t kslots, int32_t masked,
+                     int32_t kmax, int32_t n_head, int32_t dk, float temperature, float drop_p, int64_t seed, float* o,
+                     void* stream);
+int sb_attention_bwd(const float* q, const float* k, const float* v, const float* go, int64_t ld,
+                     const int64_t* batch, const int32_t* graph_ptr, const int64_t* row_ptr, int64_t N,
+                     int32_t kslots, int32_t masked, int32_t kmax, int32_t n_head, int32_t dk, float temperature,
+                     float drop_p, int64_t seed, float* gq, float* gk, float* gv, void* stream);
+/* y = LayerNorm(a + b) * w + beta per row (MaskedLN, masked_layers.py:22-32, eps 1e-6); xsum = a + b and
+ * stat[R,2] = (mean, rstd) are kept for the backward; dwb[2,C] (fp64) accumulates (dw, dbeta). */
+int sb_layernorm_fwd(const float* a, const float* b, const float* w, const float* beta, int64_t ld, int64_t R,
+                     int32_t C, float eps, float* y, float* xsum, float* stat, void* stream);
+int sb_layernorm_bwd(const float* g, const float* x, const float* stat, const float* w, int64_t ld, int64_t R,
+                     int32_t C, float* dx, double* dwb, void* stream);
 
 #ifdef __cplusplus
 }

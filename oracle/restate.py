@@ -61,9 +61,9 @@ def dense_list_evd(eig_vals: torch.Tensor, eig_vecs: torch.Tensor, batch: torch.
     N = batch.numel()
     node_ptr = np.concatenate([[0], np.cumsum(n)])
     vec_ptr = np.concatenate([[0], np.cumsum(n * n)])
-    S = np.zeros((N, nmax), dtype=np.float32)
-    V = np.zeros((N, nmax), dtype=np.float32)
     ev, evec = eig_vals.numpy(), eig_vecs.numpy()
+    S = np.zeros((N, nmax), dtype=ev.dtype)
+    V = np.zeros((N, nmax), dtype=evec.dtype)
     for b in range(len(n)):
         nb, p = int(n[b]), int(node_ptr[b])
         S[p:p + nb, :nb] = ev[p:p + nb][None, :]

@@ -39,6 +39,11 @@ _SIGNATURES = {
     "sb_segment_pool_bwd": "plpp" + "lii" + "pl" + "p",
     "sb_embedding_fwd": "plp" + "iil" + "pl" + "ip" + "p",
     "sb_embedding_bwd": "plpl" + "iil" + "pp" + "p",
+    "sb_attention_fwd": "pppl" + "ppp" + "l" + "iiiii" + "ff" + "l" + "p" + "p",
+    "sb_attention_bwd": "ppppl" + "ppp" + "l" + "iiiii" + "ff" + "l" + "ppp" + "p",
+    "sb_layernorm_fwd": "pppp" + "ll" + "i" + "f" + "ppp" + "p",
+    "sb_layernorm_bwd": "pppp" + "ll" + "i" + "pp" + "p",
+    "sb_relu_bwd": "pppl" + "p",
     "sb_slot_sum_fwd": "pll" + "i" + "ppp" + "l" + "iii" + "pl" + "i" + "p",
     "sb_slot_sum_bwd": "pl" + "pll" + "i" + "ppp" + "l" + "iii" + "i" + "p",
 }

@@ -83,8 +83,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded wait: a pipeline bug must surface as a CUDA error (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  unsigned spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xfffu) == 0 && clock64() - t0 > 4000000000ll) {
+      printf("libsignnet_b200: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, parity);
+      __trap();
+    }
   }
 }
 // global -> shared bulk copy; `bytes` multiple of 16, both addresses 16-byte aligned.

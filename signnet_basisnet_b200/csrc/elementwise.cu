@@ -424,3 +424,18 @@ extern "C" int sb_slot_sum_bwd(const float* gout, int64_t ldo, float* gx, int64_
   SB_CHECK_LAUNCH("sb_slot_sum_bwd");
   return SB_OK;
 }
+
+// out = g * [y > 0]   (backward of a ReLU fused into a Linear epilogue; out may alias g)
+__global__ void relu_bwd_kernel(const float* g, const float* __restrict__ y, float* out, long long n) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    out[t] = (__ldg(y + t) > 0.f) ? g[t] : 0.f;
+}
+extern "C" int sb_relu_bwd(const float* g, const float* y, float* out, int64_t n, void* stream) {
+  if (n == 0) return SB_OK;
+  long long blocks = sb_ceil_div(n, 256 * 4);
+  const long long cap = (long long)sb_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  relu_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, y, out, n);
+  SB_CHECK_LAUNCH("sb_relu_bwd");
+  return SB_OK;
+}

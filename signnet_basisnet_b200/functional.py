@@ -70,7 +70,7 @@ class LinearFn(torch.autograd.Function):
     """y[M, ldy] = x[M, :K] @ W[N, K]^T + b.  x may be any row stride (>= K); y is zero padded to ldy."""
 
     @staticmethod
-    def forward(ctx, x, W, b, ldy):
+    def forward(ctx, x, W, b, ldy, relu=False):
         _require_cuda(x, "x")
         x = x if x.stride(-1) == 1 and x.dim() == 2 else x.contiguous()
         W = W.contiguous()
@@ -79,16 +79,21 @@ class LinearFn(torch.autograd.Function):
             raise ValueError(f"linear: input has {x.shape[1]} columns, weight expects {K}")
         ldy = N if ldy is None else ldy
         y = torch.empty(M, ldy, dtype=torch.float32, device=x.device)
-        linear_fwd(x, x.stride(0), W, K, 1, b, y, ldy, M, 1, K, N)
-        ctx.save_for_backward(x, W)
+        linear_fwd(x, x.stride(0), W, K, 1, b, y, ldy, M, 1, K, N, relu=relu)
+        ctx.save_for_backward(x, W, y if relu else None)
         ctx.has_bias = b is not None
+        ctx.relu = relu
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, W = ctx.saved_tensors
+        x, W, y = ctx.saved_tensors
         gy = gy.contiguous()
         M, K, N = x.shape[0], W.shape[1], W.shape[0]
+        if ctx.relu:
+            gm = torch.empty_like(gy)
+            _call("sb_relu_bwd", _p(gy), _p(y), _p(gm), gy.numel())
+            gy = gm
         gx = gW = gb = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty(M, x.shape[1], dtype=torch.float32, device=x.device)
@@ -97,11 +102,31 @@ class LinearFn(torch.autograd.Function):
             gW = torch.empty_like(W)
             gb = torch.empty(N, dtype=torch.float32, device=x.device) if ctx.has_bias else None
             linear_wgrad(gy, gy.stride(0), x, x.stride(0), M, 1, N, K, gW, K, 1, gb)
-        return gx, gW, gb, None
+        return gx, gW, gb, None, None
 
 
-def linear(x, W, b=None, ldy=None):
-    return LinearFn.apply(x, W, b, ldy)
+def linear(x, W, b=None, ldy=None, relu=False):
+    return LinearFn.apply(x, W, b, ldy, relu)
+
+
+class AddFn(torch.autograd.Function):
+    """out = a + b on padded [.., ld] rows."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        ld = a.shape[-1]
+        out = torch.empty_like(a)
+        _call("sb_affine_act_res", _p(a), None, None, _p(b), _p(out), ld, a.numel() // ld, 1, ld, 0)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add_rows(a, b):
+    return AddFn.apply(a, b)
 
 
 class BatchNormActFn(torch.autograd.Function):

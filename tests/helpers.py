@@ -69,7 +69,7 @@ def assert_parity(got, ref32, ref64, tol, floor=0.0, what=""):
     `ref32` is the CPU oracle in fp32 (the reference's arithmetic), `ref64` the same oracle in fp64 ("exact").
     Pass if the CUDA result is within `tol` (1e-5 relative, BASELINE.json) of the fp32 oracle, OR — where the
     reference's own fp32 arithmetic is ill-conditioned (e.g. Linear(1->h) feeding BatchNorm with var ~ eps: the fp32
-    oracle itself is 1e-3 away from exact) — if it is no farther from the exact result than 3x the fp32 oracle is."""
+    oracle itself is 1e-3 away from exact) — if it is no farther from the exact result than 4x the fp32 oracle is."""
     got, ref32, ref64 = (t.detach().double().cpu() for t in (got, ref32, ref64))
     assert got.shape == ref64.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(ref64.shape)}"
     if got.numel() == 0:
@@ -78,7 +78,7 @@ def assert_parity(got, ref32, ref64, tol, floor=0.0, what=""):
     e_got32 = float((got - ref32).abs().max()) / scale
     e_got64 = float((got - ref64).abs().max()) / scale
     e_ref = float((ref32 - ref64).abs().max()) / scale
-    ok = e_got32 <= tol or e_got64 <= max(tol, 3.0 * e_ref)
+    ok = e_got32 <= tol or e_got64 <= max(tol, 4.0 * e_ref)
     assert ok, (f"{what}: |cuda-oracle32| {e_got32:.2e}, |cuda-exact| {e_got64:.2e}, |oracle32-exact| {e_ref:.2e} "
                 f"(tol {tol:.0e})")
 

@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — graphs/sec of the SignNet hot path (forward + backward) on ZINC-shaped synthetic batches.
+
+    python bench.py --gpus N --steps K --warmup W            # B200 path (this repo), one rank per GPU under torchrun
+    python bench.py --impl reference --steps K --warmup W    # the reference's arithmetic on the host CPU (oracle port)
+
+One JSON line on stdout (rank 0).  A "step" = zero_grad -> SignNetGNN(data) -> L1 loss -> backward on one batch of
+`--batch` graphs per GPU (weak scaling); with N > 1 the flat fp32 gradient buffer is all-reduced over NCCL every step.
+  value        device-resident: inputs already in HBM, CUDA events around K steps, max over ranks
+  e2e          through the public module API from pinned HOST buffers: H2D of the batch + step + D2H of the loss
+  roofline     phi GIN-aggregate kernel (K1): algorithmic bytes / CUDA-event duration vs measured HBM peak
+  cpu_baseline oracle port (oracle/restate.py) timed on the host cores on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "graphs/sec (SignNet fwd+bwd, ZINC-shape batch)"
+WORKLOAD = ("cfg4: ZINC-shape graphs (n~23.2, E~2.1N), SignNetGNN(PyG ZINC tree) n_hid=128 k=N_max(37) masked, "
+            "nl_signnet=8, nl_rho=1 (SetTransformer), nl_gnn=6 GINE, n_out=1; optimizer step excluded")
+CFG = dict(n_hid=128, n_out=1, nl_signnet=8, nl_gnn=6, flavour="zinc")
+
+
+def make_batch(B, seed):
+    from signnet_basisnet_b200.synth import synth_batch
+
+    d = synth_batch(B, "zinc", seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    d.y = torch.randn(B, CFG["n_out"], generator=g)
+    return d
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active")
+                                                         for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+
+    from signnet_basisnet_b200 import _lib
+    from signnet_basisnet_b200.ddp import FlatGradAllReduce
+    from signnet_basisnet_b200.sign_net import SignNetGNN
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; see --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    torch.manual_seed(0)
+    model = SignNetGNN(None, None, CFG["n_hid"], CFG["n_out"], CFG["nl_signnet"], CFG["nl_gnn"],
+                       flavour=CFG["flavour"]).to(dev).train()
+    sync = FlatGradAllReduce(model, world) if world > 1 else None
+    if sync is not None:
+        sync.broadcast_parameters()
+
+    host = make_batch(args.batch, seed=1000 + rank).pin_memory()
+    resident = host.to(dev)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.__dict__.values() if torch.is_tensor(v))
+
+    def step(data):
+        for p in model.parameters():
+            p.grad = None
+        data.__dict__.pop("_b200_graph_index", None)  # every step is a new batch: bookkeeping is part of the path
+        out = model(data)
+        loss = (out - data.y).abs().mean()
+        loss.backward()
+        if sync is not None:
+            sync.allreduce()
+        return loss
+
+    def step_e2e():
+        data = host.to(dev, non_blocking=True)
+        return float(step(data).item())  # D2H read of the loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    c0 = _lib.launch_count
+    with ClockSampler(local) as clk:
+        ms = timed(lambda: step(resident), args.steps)
+    launches = _lib.launch_count - c0
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-entry-point breakdown with CUDA events on the launching stream (separate pass, not part of `value`)
+    _lib.profile_start()
+    for _ in range(args.steps):
+        step(resident)
+    prof = _lib.profile_stop()
+    total_prof = sum(t for _, t in prof.values()) or 1.0
+    kernels = [{"entry": k, "launches_per_step": c / args.steps, "ms_per_step": t / args.steps,
+                "share": t / total_prof} for k, (c, t) in sorted(prof.items(), key=lambda kv: -kv[1][1])][:12]
+
+    # roofline of the phi aggregate (K1): bytes = 2*4*ld*S*R + 16*E per launch, forward launches
+    gi = resident._b200_graph_index
+    sl = gi.slots_all(CFG["n_hid"])
+    agg_bytes = 2 * 4 * CFG["n_hid"] * 2 * sl.R + 16 * gi.E
+    peak, peak_src = peaks()
+    roof = None
+    tag = f"sb_gin_agg[ld={CFG['n_hid']}]"
+    if tag in prof:
+        c, t = prof[tag]
+        ach = agg_bytes / (t / c * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "agg_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        roof = {"kernel": "gin_agg_tma_kernel (phi aggregate, forward)", "bound": "hbm", "achieved": round(ach, 1),
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / peak, 4),
+                "traffic": traffic, "algorithmic_bytes_per_launch": agg_bytes,
+                "avg_launch_us": round(t / c * 1e3, 1), "launches_per_step": c / args.steps,
+                "slot_rows_R": sl.R, "dense_slot_bytes_per_launch": 2 * 4 * CFG["n_hid"] * 2 * gi.N * sl.k + 16 * gi.E}
+        btag = f"sb_gin_agg[ld={CFG['n_hid']},bwd]"
+        if btag in prof:
+            cb, tb = prof[btag]
+            bb = 4 * 4 * CFG["n_hid"] * 2 * sl.R + 16 * gi.E  # dA, G, X in; G out
+            roof["backward"] = {"achieved": round(bb / (tb / cb * 1e-3) / 1e9, 1), "bytes_per_launch": bb,
+                                "avg_launch_us": round(tb / cb * 1e3, 1)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    graphs = args.batch * world * args.steps
+    line = {
+        "metric": METRIC, "value": round(graphs / (ms * 1e-3), 1), "unit": "graphs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "graphs_per_gpu": args.batch, "global_batch": args.batch * world,
+                   "nodes_per_gpu": gi.N, "edges_per_gpu": gi.E, "parallelism": f"dp{world}",
+                   "l2": "working set per step (>= 0.6 GB per activation tensor) exceeds the 126 MB L2",
+                   "weights": "random init (reference default init, seed 0)"},
+        "e2e": {"value": round(graphs / (ms_e2e * 1e-3), 1), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": launches, "gpu_launches_note": "C-ABI entry-point calls inside the timed region (each "
+                                                        "enqueues >= 1 kernel of libsignnet_b200.so)",
+        "clocks": clk.summary(), "roofline": roof, "kernels": kernels,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------- CPU arm (oracle port)
+def _oracle_step_fn(B, seed=1000):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import restate  # the CPU restatement of the reference's arithmetic (test infrastructure, used here as the baseline)
+
+    from signnet_basisnet_b200.sign_net import SignNetGNN
+
+    torch.manual_seed(0)
+    model = SignNetGNN(None, None, CFG["n_hid"], CFG["n_out"], CFG["nl_signnet"], CFG["nl_gnn"], flavour=CFG["flavour"])
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    d = make_batch(B, seed)
+
+    def step():
+        for v in sd.values():
+            if v.requires_grad:
+                v.grad = None
+        out = restate.sign_net_gnn(d, sd, CFG["nl_signnet"], CFG["nl_gnn"], nl_rho=1, ignore_eigval=True, training=True,
+                                   attn_dropout=0.1)
+        loss = (out - d.y).abs().mean()
+        loss.backward()
+        return float(loss)
+
+    return step
+
+
+def cpu_baseline(B):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = _oracle_step_fn(B)
+    step()  # warm-up
+    t0 = time.perf_counter()
+    step()
+    dt = time.perf_counter() - t0
+    return {"value": round(B / dt, 2), "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"1 warm-up + 1 timed fwd+bwd step of the same model on {B} ZINC-shape graphs "
+                      f"(oracle/restate.py, torch CPU fp32, {dt:.1f} s)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    B = args.cpu_sample
+    step = _oracle_step_fn(B)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = round(B * steps / dt, 2)
+    sample = (f"{steps} timed steps (after warm-up) of fwd+bwd on {B} ZINC-shape graphs per step with the oracle port "
+              f"of the reference (torch CPU fp32, all host threads)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "graphs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(dt / steps * 1e3, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "graphs_per_step": B},
+        "cpu_baseline": {"value": v, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="graphs per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="graphs per step of the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

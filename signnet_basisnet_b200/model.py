@@ -229,6 +229,8 @@ class GNN(nn.Module):
         super().__init__()
         if gnn_type != "GINEConv":
             raise ValueError("only GINEConv is on the SignNet hot path (main_alchemy.py:35)")
+        if pooling != "add":
+            raise NotImplementedError("pooling='add' is the only read-out the shipped configurations use")
         if dropout != 0:
             raise NotImplementedError("dropout is 0 in every shipped configuration")
         mk_disc = lambda: DiscreteEncoder(nhid, max_num_values=max_num_values)
@@ -239,6 +241,8 @@ class GNN(nn.Module):
         self.norms = nn.ModuleList([nn.BatchNorm1d(nhid) if bn else Identity() for _ in range(nlayer)])
         self.output_encoder = MLP(nhid, nout, nlayer=2, with_final_activation=False,
                                   with_norm=False if pooling == "mean" else True)
+        if max_num_values != 6:  # GINESignNetPyG flavour: allocated, used only for mean pooling (core/model.py:18,72)
+            self.size_embedder = nn.Embedding(200, nhid)
         self.linear = nn.Linear(2 * nhid, nhid)
         self.pooling, self.dropout, self.res, self.bn = pooling, dropout, res, bn
         self.nhid, self.nout = nhid, nout

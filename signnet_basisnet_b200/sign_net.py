@@ -126,11 +126,17 @@ class GNN3d(nn.Module):
             raise ValueError(flavour)
         self.convs = nn.ModuleList([mk(i) for i in range(n_layer)])
         self.norms = nn.ModuleList([MaskedBN(n_out) for _ in range(n_layer)])
+        if flavour == "zinc":  # allocated by the reference, never run (core/sign_net.py:22,37-39; quirk v)
+            from .model import DiscreteEncoder
+            self.edge_encoders = nn.ModuleList([DiscreteEncoder(n_in if i == 0 else n_out, max_num_values=500)
+                                                for i in range(n_layer)])
 
     def reset_parameters(self):
         for conv, norm in zip(self.convs, self.norms):
             conv.reset_parameters()
             norm.reset_parameters()
+        for enc in getattr(self, "edge_encoders", []):
+            enc.reset_parameters()
 
     # ------------------------------------------------------------------------------------------------ execution
     def _flat_params(self):
@@ -189,8 +195,10 @@ class SetTransformer(nn.Module):
     """rho of the PyG trees (sign_net.py:46-72).  Round-1 scope: the nl_rho = 0 form (sum over slots -> Linear -> BN)
     runs on the B200 kernels; the attention layers are SURVEY §8f rank 1 ("next")."""
 
-    def __init__(self, nhid, nlayer):
+    def __init__(self, nhid, nlayer, flavour="alchemy"):
         super().__init__()
+        if flavour == "zinc":  # allocated by the reference, never run (core/sign_net.py:54; quirk v)
+            self.pos_encoder = MaskedMLP(1, nhid, nlayer=2)
         if nlayer > 0:
             from .transformer import TransformerEncoderLayer
             self.transformer_layers = nn.ModuleList(TransformerEncoderLayer(nhid, n_head=4) for _ in range(nlayer))
@@ -228,7 +236,7 @@ class SignNet(nn.Module):
     def __init__(self, n_hid, nl_phi, nl_rho=2, ignore_eigval=False, flavour="alchemy"):
         super().__init__()
         self.phi = GNN3d(1, n_hid, nl_phi, gnn_type="MaskedGINConv", flavour=flavour)
-        self.rho = SetTransformer(n_hid, nl_rho)
+        self.rho = SetTransformer(n_hid, nl_rho, flavour=flavour)
         self.flavour = flavour
         self.ignore_eigval = ignore_eigval if flavour == "alchemy" else True
         self.n_hid = n_hid

@@ -104,6 +104,9 @@ int sb_gin_agg_tile_rows(int32_t ld); /* rows per shared-memory tile of the TMA 
 int sb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t w_rs, int64_t w_cs, const float* bias,
                   float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N, int32_t pro, const float* pa,
                   const float* pc, int32_t relu, double* stats, int32_t accumulate, void* stream);
+/* 1: contractions with 16 <= K,N <= 128 run on tcgen05 (3xTF32, linear_tc.cu); 0: fp32 FFMA everywhere.  Returns the
+ * previous setting (-1 = not yet decided; env SB_DISABLE_TC=1 also selects FFMA). */
+int sb_set_tensor_cores(int32_t enable);
 /* dw[n*rs + k*cs] (+)= sum gy[., n] * f(x[., k]);  db[n] (+)= sum gy[., n]   (deterministic two-stage reduction) */
 int sb_linear_wgrad(const float* gy, int64_t ldg, const float* x, int64_t ldx, int64_t R, int32_t G, int32_t N,
                     int32_t K, int32_t pro, const float* pa, const float* pc, float* dw, int64_t dw_rs,

@@ -70,6 +70,8 @@ def lib():
         L.sb_gin_agg_tile_rows.restype = ctypes.c_int
         L.sb_gin_agg_tile_rows.argtypes = [ctypes.c_int32]
         L.sb_linear_wgrad_workspace_floats.restype = ctypes.c_int64
+        L.sb_set_tensor_cores.restype = ctypes.c_int
+        L.sb_set_tensor_cores.argtypes = [ctypes.c_int32]
         L.sb_embedding_bwd_workspace_floats.restype = ctypes.c_int64
         L.sb_embedding_bwd_workspace_floats.argtypes = [ctypes.c_int32, ctypes.c_int32]
         for name, sig in _SIGNATURES.items():
@@ -82,7 +84,8 @@ def lib():
 
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["sb_last_error", "sb_abi_version", "sb_device_sm_count", "sb_gin_agg_tile_rows",
-                                       "sb_linear_wgrad_workspace_floats", "sb_embedding_bwd_workspace_floats"])
+                                       "sb_linear_wgrad_workspace_floats", "sb_embedding_bwd_workspace_floats",
+                                       "sb_set_tensor_cores"])
 
 
 def ptr(t):
@@ -122,6 +125,10 @@ def counted_call(name, *args):
 def _profile_tag(name, args):
     if name == "sb_gin_agg":  # (.., R, B, k, masked, S, ld, tile_rows, force_generic): split by row width / path
         return f"sb_gin_agg[ld={args[16]}{',generic' if args[18] else ''}{',bwd' if args[2] or args[3] else ''}]"
+    if name == "sb_linear_fwd":    # (x, ldx, w, rs, cs, bias, y, ldy, R, G, K, N, pro, ...)
+        return f"sb_linear_fwd[K={args[10]},N={args[11]},rows={args[8] * args[9]}]"
+    if name == "sb_linear_wgrad":  # (gy, ldg, x, ldx, R, G, N, K, ...)
+        return f"sb_linear_wgrad[N={args[6]},K={args[7]},rows={args[4] * args[5]}]"
     return name
 
 

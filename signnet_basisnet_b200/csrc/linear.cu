@@ -14,6 +14,8 @@
 #include "common.cuh"
 #include "../../include/signnet_b200.h"
 
+#include <stdlib.h>
+
 #define LIN_BM 128
 #define LIN_BK 32
 #define LIN_BKP 36
@@ -254,6 +256,25 @@ static size_t lin_smem_bytes(int KP, int BN) {
   return ((size_t)KP * BN + 2 * LIN_BM * LIN_BKP) * sizeof(float) + (size_t)LIN_MAXG * 2 * BN * sizeof(double);
 }
 
+// tensor-core path (linear_tc.cu)
+int sb_linear_tc_launch(const float* x, int64_t ldx, const float* w, int64_t w_rs, int64_t w_cs, const float* bias,
+                        float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N, int32_t pro,
+                        const float* pa, const float* pc, int32_t relu, double* stats, int32_t accumulate,
+                        int32_t ycols, cudaStream_t st);
+static int g_use_tc = -1;
+extern "C" int sb_set_tensor_cores(int32_t enable) {
+  const int old = g_use_tc;
+  g_use_tc = enable ? 1 : 0;
+  return old;
+}
+static bool use_tc() {
+  if (g_use_tc < 0) {
+    const char* e = getenv("SB_DISABLE_TC");
+    g_use_tc = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_use_tc == 1;
+}
+
 template <int BN>
 static int launch_linear(const LinArgs& a, cudaStream_t st) {
   static size_t configured = 0;
@@ -306,7 +327,12 @@ extern "C" int sb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_
       a.yvec = (ldy % 4 == 0) && ((uintptr_t)a.y % 16 == 0);
       const bool last_n = (n0 + 128 >= N);
       a.ycols = last_n ? (int)((ldy - n0 < 128) ? (ldy - n0) : 128) : 128;
-      int rc = (nn <= 64 && a.ycols <= 64) ? launch_linear<64>(a, st) : launch_linear<128>(a, st);
+      int rc = SB_ERR_UNSUPPORTED;
+      if (use_tc())
+        rc = sb_linear_tc_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro, a.pa,
+                                 a.pc, a.relu, a.stats, a.accumulate, a.ycols, st);
+      if (rc == SB_ERR_UNSUPPORTED)
+        rc = (nn <= 64 && a.ycols <= 64) ? launch_linear<64>(a, st) : launch_linear<128>(a, st);
       if (rc != SB_OK) return rc;
     }
   }

@@ -1,23 +1,26 @@
 // K2 on the 5th-generation tensor cores: y = f(x) W^T (+ bias, relu, column statistics) with tcgen05.mma kind::tf32
-// and error-compensated operands (3xTF32):  x = xh + xl, w = wh + wl with xh/wh the tf32-representable heads, and
+// and error-compensated operands (3xTF32):  x = xh + xl, w = wh + wl with xh/wh the tf32-rounded heads, and
 //     x w  ~=  xh wh + xh wl + xl wh        (fp32 accumulation in tensor memory)
 // which keeps the result within ~1e-6 relative of an fp32 FFMA contraction — BASELINE.json's 1e-5 parity bar rules out
 // a single-pass TF32/bf16 product.  Same contract as linear_fwd_kernel (linear.cu): prologue none | BN-affine |
-// BN-affine+ReLU applied once per element on load, epilogue bias / ReLU / per-(group, channel) fp64 column sums.
+// BN-affine+ReLU applied once per element, epilogue bias / ReLU / per-(group, channel) fp64 column sums.
 //
-// One persistent CTA per SM.  The weight matrix (<= 128 x 128) is split once and stays in shared memory in the
-// canonical K-major SWIZZLE_128B layout (head and tail: 128 KB); activation row tiles of 128 rows are streamed as
-// 32-float K-blocks through a 2-stage ring (global -> registers -> prologue -> split -> swizzled st.shared), thread 0
-// issues the MMAs (UMMA 128 x N x 8, accumulator = 128 TMEM columns) and tcgen05.commit recycles the ring stages
-// through mbarriers; the epilogue drains TMEM with tcgen05.ld, stages the tile in the (idle) ring and writes it back
-// with coalesced 128-bit stores while accumulating the BatchNorm column sums.
+// One persistent CTA per SM, warp-specialised:
+//   warps 0..15  workers: whole-tile register prefetch of the NEXT 128-row tile (64 KB of HBM reads in flight per SM),
+//                prologue + head/tail split + swizzled st.shared of one 32-float K-block at a time into a 2-stage ring,
+//                then the epilogue: tcgen05.ld (one 32x32 block per warp) -> bias/ReLU -> shared staging (the idle
+//                ring) -> coalesced 128-bit stores + fp64 column sums for the BatchNorm that follows;
+//   warp 16      MMA issuer: waits full[stage], issues 12 x UMMA 128 x N x 8 (kind::tf32) per K-block against the
+//                resident weight (head and tail, canonical K-major SWIZZLE_128B, 128 KB), tcgen05.commit recycles the
+//                ring stage (mma_done) and publishes the accumulator (acc_done).
 #include "common.cuh"
 #include "../../include/signnet_b200.h"
 
 #define TC_BM 128
 #define TC_KB 32                      // floats per K-block = one 128-byte swizzle row
 #define TC_BLK_BYTES (128 * 128)      // one [128 rows x 32 floats] operand block
-#define TC_THREADS 256
+#define TC_WORKERS 512
+#define TC_THREADS (TC_WORKERS + 32)
 #define TC_MAXG 2
 
 struct TcArgs {
@@ -67,6 +70,7 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem, uint64_t da, uint64_t db, 
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory"); }
 #define TC_LD32(v, taddr)                                                                                              \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                             \
                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26," \
@@ -86,8 +90,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
   uint8_t* ring = Wl + nkb * TC_BLK_BYTES;         // 2 stages x (head 16 KB | tail 16 KB) = 64 KB; reused as the
                                                    // [128][128] fp32 staging tile of the epilogue
   __shared__ double sacc[TC_MAXG * 2 * 128];
-  __shared__ uint64_t mma_done[2];
-  __shared__ uint64_t acc_done;
+  __shared__ float s_pa[TC_MAXG * 128], s_pc[TC_MAXG * 128], s_bias[128];
+  __shared__ uint64_t full[2], mma_done[2], acc_done;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -106,15 +110,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
     *reinterpret_cast<float*>(Wh + off) = h;
     *reinterpret_cast<float*>(Wl + off) = l;
   }
-  if (a.stats)
-    for (int idx = tid; idx < TC_MAXG * 2 * 128; idx += TC_THREADS) sacc[idx] = 0.0;
+  for (int idx = tid; idx < TC_MAXG * 128; idx += TC_THREADS) {
+    const int g = idx >> 7, c = idx & 127;
+    const bool ok = a.pro && g < a.G && c < K;
+    s_pa[idx] = ok ? __ldg(a.pa + (long long)g * K + c) : 1.f;
+    s_pc[idx] = ok ? __ldg(a.pc + (long long)g * K + c) : 0.f;
+  }
+  for (int idx = tid; idx < 128; idx += TC_THREADS) s_bias[idx] = (a.bias && idx < N) ? __ldg(a.bias + idx) : 0.f;
+  for (int idx = tid; idx < TC_MAXG * 2 * 128; idx += TC_THREADS) sacc[idx] = 0.0;
   if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
     mbar_init(&mma_done[0], 1);
     mbar_init(&mma_done[1], 1);
     mbar_init(&acc_done, 1);
     mbar_fence_init();
   }
-  if (warp == 0) {
+  if (warp == 16) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -123,125 +135,134 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.NP >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
   const long long tpg = (a.R + TC_BM - 1) / TC_BM;
   const long long ntiles = tpg * a.G;
 
-  // Whole-tile register prefetch: all 4 K-blocks (64 KB per CTA) of the NEXT row tile are requested before the
-  // epilogue of the current one, so ~64 KB of HBM reads are in flight per SM at any time.
-  float4 pre[16];
-  auto load_tile = [&](long long tile) {   // raw loads only: nothing here may depend on the loaded values
-    const int g = (int)(tile / tpg);
-    const long long row0 = (tile - (long long)g * tpg) * TC_BM;
-    const int rows = (int)((a.R - row0 < TC_BM) ? (a.R - row0) : TC_BM);
-    const long long base = (long long)g * a.R + row0;
+  if (warp == 16) {
+    // =============================================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc =
+          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.NP >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      unsigned cnt = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+          const int stage = cnt & 1;
+          mbar_wait(&full[stage], (cnt >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ah = smem_u32(ring + stage * 2 * TC_BLK_BYTES), al = ah + TC_BLK_BYTES;
+          const uint32_t wh = smem_u32(Wh + kb * TC_BLK_BYTES), wl = smem_u32(Wl + kb * TC_BLK_BYTES);
 #pragma unroll
-    for (int kb = 0; kb < 4; ++kb) {
-      if (kb >= nkb) break;
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t o = j * 32;
+            tc_mma(tmem, tc_make_desc(ah + o), tc_make_desc(wh + o), idesc, (kb | j) ? 1u : 0u);
+            tc_mma(tmem, tc_make_desc(ah + o), tc_make_desc(wl + o), idesc, 1u);
+            tc_mma(tmem, tc_make_desc(al + o), tc_make_desc(wh + o), idesc, 1u);
+          }
+          tc_commit(&mma_done[stage]);
+          if (kb == nkb - 1) tc_commit(&acc_done);
+        }
+      }
+    }
+  } else {
+    // ================================================================================================== workers
+    // Whole-tile register prefetch (raw loads only: nothing here may depend on the loaded values).
+    float4 pre[8];
+    auto load_tile = [&](long long tile) {
+      const int g = (int)(tile / tpg);
+      const long long row0 = (tile - (long long)g * tpg) * TC_BM;
+      const int rows = (int)((a.R - row0 < TC_BM) ? (a.R - row0) : TC_BM);
+      const long long base = (long long)g * a.R + row0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int f = tid + TC_THREADS * q;
+      for (int kb = 0; kb < 4; ++kb) {
+        if (kb >= nkb) break;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int f = tid + TC_WORKERS * q;
+          const int row = f >> 3, c4 = f & 7;
+          const int col = kb * TC_KB + c4 * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < rows && col < K) {
+            const float* p = a.x + (base + row) * a.ldx + col;
+            if (a.xvec) {
+              v = ldg4(p);
+            } else {
+              v.x = __ldg(p);
+              if (col + 1 < K) v.y = __ldg(p + 1);
+              if (col + 2 < K) v.z = __ldg(p + 2);
+              if (col + 3 < K) v.w = __ldg(p + 3);
+            }
+          }
+          pre[kb * 2 + q] = v;
+        }
+      }
+    };
+    // prologue (BatchNorm affine / ReLU) + zeroing of the K tail + head/tail split, applied when a block is consumed
+    auto store_block = [&](int stage, int kb, int g, int rows) {
+      uint8_t* sh = ring + stage * 2 * TC_BLK_BYTES;
+      uint8_t* sl = sh + TC_BLK_BYTES;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int f = tid + TC_WORKERS * q;
         const int row = f >> 3, c4 = f & 7;
         const int col = kb * TC_KB + c4 * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < rows && col < K) {
-          const float* p = a.x + (base + row) * a.ldx + col;
-          if (a.xvec) {
-            v = ldg4(p);
-          } else {
-            v.x = __ldg(p);
-            if (col + 1 < K) v.y = __ldg(p + 1);
-            if (col + 2 < K) v.z = __ldg(p + 2);
-            if (col + 3 < K) v.w = __ldg(p + 3);
-          }
-        }
-        pre[kb * 4 + q] = v;
-      }
-    }
-  };
-  // prologue (BatchNorm affine / ReLU) + zeroing of the K tail + head/tail split, applied when a K-block is consumed
-  auto store_block = [&](int stage, int kb, int g, int rows) {
-    uint8_t* sh = ring + stage * 2 * TC_BLK_BYTES;
-    uint8_t* sl = sh + TC_BLK_BYTES;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int f = tid + TC_THREADS * q;
-      const int row = f >> 3, c4 = f & 7;
-      const int col = kb * TC_KB + c4 * 4;
-      const float4 pv = (kb == 0) ? pre[q] : (kb == 1) ? pre[4 + q] : (kb == 2) ? pre[8 + q] : pre[12 + q];
-      float t[4] = {pv.x, pv.y, pv.z, pv.w};
-      const bool live = row < rows;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (live && col + j < K) {
-          if (a.pro) {
-            const float u = fmaf(__ldg(a.pa + (long long)g * K + col + j), t[j], __ldg(a.pc + (long long)g * K + col + j));
-            t[j] = (a.pro == 2) ? fmaxf(u, 0.f) : u;
-          }
-        } else {
-          t[j] = 0.f;
-        }
-      }
-      float4 h, l;
-      tc_split(t[0], h.x, l.x);
-      tc_split(t[1], h.y, l.y);
-      tc_split(t[2], h.z, l.z);
-      tc_split(t[3], h.w, l.w);
-      const uint32_t off = tc_sw128(row, c4);
-      *reinterpret_cast<float4*>(sh + off) = h;
-      *reinterpret_cast<float4*>(sl + off) = l;
-    }
-  };
-
-  long long tile = blockIdx.x;
-  unsigned cnt = 0;        // K-blocks issued so far by this CTA (ring position = cnt & 1, use index = cnt >> 1)
-  unsigned tile_it = 0;
-  if (tile < ntiles) load_tile(tile);
-
-  while (tile < ntiles) {
-    const int g = (int)(tile / tpg);
-    const long long row0 = (tile - (long long)g * tpg) * TC_BM;
-    const int rows = (int)((a.R - row0 < TC_BM) ? (a.R - row0) : TC_BM);
-    const long long base = (long long)g * a.R + row0;
-    const long long ntile = tile + gridDim.x;
-
-    for (int kb = 0; kb < nkb; ++kb, ++cnt) {
-      const int stage = cnt & 1;
-      const unsigned use = cnt >> 1;
-      if (use > 0) mbar_wait(&mma_done[stage], (use - 1) & 1);   // MMAs that read this stage have retired
-      store_block(stage, kb, g, rows);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      // the registers of this tile are consumed: request the whole next tile while the tensor core + epilogue run
-      if (kb == nkb - 1 && ntile < ntiles) load_tile(ntile);
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t ah = smem_u32(ring + stage * 2 * TC_BLK_BYTES), al = ah + TC_BLK_BYTES;
-        const uint32_t wh = smem_u32(Wh + kb * TC_BLK_BYTES), wl = smem_u32(Wl + kb * TC_BLK_BYTES);
+        const float4 pv = (kb == 0) ? pre[q] : (kb == 1) ? pre[2 + q] : (kb == 2) ? pre[4 + q] : pre[6 + q];
+        float t[4] = {pv.x, pv.y, pv.z, pv.w};
+        const bool live = row < rows;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t o = j * 32;
-          tc_mma(tmem, tc_make_desc(ah + o), tc_make_desc(wh + o), idesc, (kb | j) ? 1u : 0u);
-          tc_mma(tmem, tc_make_desc(ah + o), tc_make_desc(wl + o), idesc, 1u);
-          tc_mma(tmem, tc_make_desc(al + o), tc_make_desc(wh + o), idesc, 1u);
+          if (live && col + j < K) {
+            if (a.pro) {
+              const float u = fmaf(s_pa[g * 128 + col + j], t[j], s_pc[g * 128 + col + j]);
+              t[j] = (a.pro == 2) ? fmaxf(u, 0.f) : u;
+            }
+          } else {
+            t[j] = 0.f;
+          }
         }
-        tc_commit(&mma_done[stage]);
-        if (kb == nkb - 1) tc_commit(&acc_done);
+        float4 h, l;
+        tc_split(t[0], h.x, l.x);
+        tc_split(t[1], h.y, l.y);
+        tc_split(t[2], h.z, l.z);
+        tc_split(t[3], h.w, l.w);
+        const uint32_t off = tc_sw128(row, c4);
+        *reinterpret_cast<float4*>(sh + off) = h;
+        *reinterpret_cast<float4*>(sl + off) = l;
       }
-    }
+    };
 
-    // ------------------------------------------------------------------------------------------------ epilogue
-    mbar_wait(&acc_done, tile_it & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* stg = reinterpret_cast<float*>(ring);   // [128][128] fp32, float4 chunk index XOR (row & 31)
-    {
-      const int q = warp & 3, hf = warp >> 2;       // TMEM lane quarter, column half
-      const int row = q * 32 + lane;
-#pragma unroll
-      for (int part = 0; part < 2; ++part) {
-        const int c0 = hf * 64 + part * 32;
+    long long tile = blockIdx.x;
+    unsigned cnt = 0, tile_it = 0;
+    if (tile < ntiles) load_tile(tile);
+
+    while (tile < ntiles) {
+      const int g = (int)(tile / tpg);
+      const long long row0 = (tile - (long long)g * tpg) * TC_BM;
+      const int rows = (int)((a.R - row0 < TC_BM) ? (a.R - row0) : TC_BM);
+      const long long base = (long long)g * a.R + row0;
+      const long long ntile = tile + gridDim.x;
+
+      for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+        const int stage = cnt & 1;
+        const unsigned use = cnt >> 1;
+        if (use > 0) mbar_wait(&mma_done[stage], (use - 1) & 1);   // MMAs that read this stage have retired
+        store_block(stage, kb, g, rows);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        worker_sync();
+        if (tid == 0) mbar_arrive(&full[stage]);
+      }
+      // registers of this tile are consumed: request the whole next tile while the tensor core + epilogue run
+      if (ntile < ntiles) load_tile(ntile);
+
+      // ---------------------------------------------------------------------------------------------- epilogue
+      mbar_wait(&acc_done, tile_it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float* stg = reinterpret_cast<float*>(ring);   // [128][128] fp32, float4 chunk index XOR (row & 31)
+      {
+        const int q = warp & 3, cb = warp >> 2;       // TMEM lane quarter, 32-column block
+        const int row = q * 32 + lane;
+        const int c0 = cb * 32;
         if (c0 < a.NP) {
           uint32_t v[32];
           TC_LD32(v, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0);
@@ -252,70 +273,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int col = c0 + i * 4 + j;
-              float t = __uint_as_float(v[i * 4 + j]);
-              if (col < N) {
-                if (a.bias) t += __ldg(a.bias + col);
-                if (a.accumulate && row < rows) t += a.y[(base + row) * a.ldy + col];
-                if (a.relu) t = fmaxf(t, 0.f);
-              } else {
-                t = 0.f;
-              }
-              o[j] = t;
+              float t = __uint_as_float(v[i * 4 + j]) + s_bias[col];
+              if (a.accumulate && row < rows && col < N) t += a.y[(base + row) * a.ldy + col];
+              if (a.relu) t = fmaxf(t, 0.f);
+              o[j] = (col < N) ? t : 0.f;
             }
             const int ch = (c0 >> 2) + i;
             *reinterpret_cast<float4*>(stg + row * 128 + ((ch ^ (row & 31)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
       }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    // coalesced write-back: one warp per row, lanes over float4 chunks
-    for (int row = warp; row < rows; row += TC_THREADS / 32) {
-      const int col0 = lane * 4;
-      if (col0 < a.ycols) {
-        const float4 o = *reinterpret_cast<const float4*>(stg + row * 128 + ((lane ^ (row & 31)) << 2));
-        float* yrow = a.y + (base + row) * a.ldy;
-        if (a.yvec) {
-          *reinterpret_cast<float4*>(yrow + col0) = o;
-        } else {
-          const float t[4] = {o.x, o.y, o.z, o.w};
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      worker_sync();
+      // coalesced write-back: one warp per row (8 rows per warp), lanes over float4 chunks
+      {
+        const int col0 = lane * 4;
+        if (col0 < a.ycols) {
+#pragma unroll 4
+          for (int row = warp; row < rows; row += TC_WORKERS / 32) {
+            const float4 o = *reinterpret_cast<const float4*>(stg + row * 128 + ((lane ^ (row & 31)) << 2));
+            float* yrow = a.y + (base + row) * a.ldy;
+            if (a.yvec) {
+              *reinterpret_cast<float4*>(yrow + col0) = o;
+            } else {
+              const float t[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (col0 + j < a.ycols) yrow[col0 + j] = t[j];
+              for (int j = 0; j < 4; ++j)
+                if (col0 + j < a.ycols) yrow[col0 + j] = t[j];
+            }
+          }
         }
       }
-    }
-    if (a.stats) {
-      // column sums in fp64: thread -> (column, row half)
-      const int col = tid & 127, half = tid >> 7;
-      if (col < N) {
-        double s = 0.0, q2 = 0.0;
-        const int r_end = (rows < (half + 1) * 64) ? rows : (half + 1) * 64;
-        for (int row = half * 64; row < r_end; ++row) {
-          const float t = stg[row * 128 + ((((col >> 2) ^ (row & 31)) << 2) | (col & 3))];
-          s += (double)t;
-          q2 += (double)t * (double)t;
+      if (a.stats) {
+        // column sums in fp64: thread -> (column, row quarter); two independent chains per thread
+        const int col = tid & 127, part = tid >> 7;
+        if (col < N) {
+          double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
+          const int r_beg = part * 32;
+          const int r_end = (rows < r_beg + 32) ? rows : r_beg + 32;
+          int row = r_beg;
+          for (; row + 1 < r_end; row += 2) {
+            const float t0 = stg[row * 128 + ((((col >> 2) ^ (row & 31)) << 2) | (col & 3))];
+            const float t1 = stg[(row + 1) * 128 + ((((col >> 2) ^ ((row + 1) & 31)) << 2) | (col & 3))];
+            s0 += (double)t0; q0 += (double)t0 * (double)t0;
+            s1 += (double)t1; q1 += (double)t1 * (double)t1;
+          }
+          if (row < r_end) {
+            const float t0 = stg[row * 128 + ((((col >> 2) ^ (row & 31)) << 2) | (col & 3))];
+            s0 += (double)t0; q0 += (double)t0 * (double)t0;
+          }
+          atomicAdd(&sacc[(g * 2 + 0) * 128 + col], s0 + s1);
+          atomicAdd(&sacc[(g * 2 + 1) * 128 + col], q0 + q1);
         }
-        atomicAdd(&sacc[(g * 2 + 0) * 128 + col], s);
-        atomicAdd(&sacc[(g * 2 + 1) * 128 + col], q2);
       }
+      worker_sync();   // staging (= ring) is free again; the TMEM accumulator has been drained
+      tile = ntile;
+      ++tile_it;
     }
-    __syncthreads();   // staging (= ring) is free again; TMEM accumulator has been drained
-    tile = ntile;
-    ++tile_it;
   }
 
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
   if (a.stats) {
-    __syncthreads();
     for (int idx = tid; idx < a.G * 2 * 128; idx += TC_THREADS) {
       const int col = idx & 127, gj = idx >> 7;
       if (col < N && sacc[idx] != 0.0) atomicAdd(a.stats + (long long)gj * N + col, sacc[idx]);
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+  if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
 }
 
 // Returns SB_ERR_UNSUPPORTED (without setting an error) when the shape is better served by the FFMA kernel.

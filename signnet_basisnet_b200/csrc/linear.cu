@@ -540,6 +540,18 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part_w, const floa
   }
 }
 
+int sb_wgrad_reduce_launch(const float* part_w, const float* part_b, int nparts, int BN, int BK, int N, int K, float* dw,
+                           long long rs, long long cs, float* db, int accumulate, cudaStream_t st) {
+  const int total = N * K + (db ? N : 0);
+  wgrad_reduce_kernel<<<(unsigned)sb_ceil_div(total, 128), 128, 0, st>>>(part_w, part_b, nparts, BN, BK, N, K, dw, rs, cs,
+                                                                        db, accumulate);
+  SB_CHECK_LAUNCH("sb_linear_wgrad(reduce)");
+  return SB_OK;
+}
+int sb_wgrad_tc_launch(const float* gy, int64_t ldg, const float* x, int64_t ldx, int64_t R, int32_t G, int32_t N,
+                       int32_t K, int32_t pro, const float* pa, const float* pc, float* dw, int64_t dw_rs,
+                       int64_t dw_cs, float* db, int32_t accumulate, float* workspace, cudaStream_t st);
+
 template <int BN, int BK>
 static int launch_wgrad(WgArgs a, int N, int K, float* dw, long long rs, long long cs, float* db, int accumulate,
                         float* workspace, cudaStream_t st) {
@@ -597,7 +609,14 @@ extern "C" int sb_linear_wgrad(const float* gy, int64_t ldg, const float* x, int
       a.part_w = nullptr; a.part_b = nullptr;
       float* dwp = dw + (long long)n0 * dw_rs + (long long)k0 * dw_cs;
       float* dbp = (db && k0 == 0) ? db + n0 : nullptr;
-      int rc;
+      int rc = SB_ERR_UNSUPPORTED;
+      if (use_tc())
+        rc = sb_wgrad_tc_launch(a.g, a.ldg, a.x, a.ldx, a.R, a.G, a.N, a.K, a.pro, a.pa, a.pc, dwp, dw_rs, dw_cs, dbp,
+                                accumulate, workspace, st);
+      if (rc != SB_ERR_UNSUPPORTED) {
+        if (rc != SB_OK) return rc;
+        continue;
+      }
       if (nn <= 64 && kk <= 64) rc = launch_wgrad<64, 64>(a, nn, kk, dwp, dw_rs, dw_cs, dbp, accumulate, workspace, st);
       else if (nn <= 64) rc = launch_wgrad<64, 128>(a, nn, kk, dwp, dw_rs, dw_cs, dbp, accumulate, workspace, st);
       else if (kk <= 64) rc = launch_wgrad<128, 64>(a, nn, kk, dwp, dw_rs, dw_cs, dbp, accumulate, workspace, st);

@@ -309,14 +309,39 @@ extern "C" int sb_bn_bwd_finalize(const double* stats, int64_t M, int32_t G, int
   return SB_OK;
 }
 
-// out = al[g,c]*t1 + be[g,c]*(t2 - mean[g,c]) + ga[g,c]  evaluated in fp64, rounded once (out may alias t1)
+// out = al[g,c]*t1 + be[g,c]*(t2 - mean[g,c]) + ga[g,c]   (out may alias t1).
+// The fp64 coefficients are carried as unevaluated float pairs (hi + lo) and applied with two FMAs each, so the
+// coefficient itself contributes no systematic fp32 rounding (see bn_bwd_finalize_kernel) while the kernel stays an
+// HBM-bound fp32 stream; t2 - mean is formed against the float pair of the fp64 mean.
+struct F2 { float hi, lo; };
+__device__ __forceinline__ F2 split_d(double v) {
+  F2 r;
+  r.hi = (float)v;
+  r.lo = (float)(v - (double)r.hi);
+  return r;
+}
 __global__ void __launch_bounds__(EW_THREADS) affine2_kernel(const float* t1, const float* __restrict__ t2,
                                                              const double* __restrict__ coef,
                                                              const double* __restrict__ mean_rstd, float* out,
                                                              long long ld, long long R, int G, int C) {
+  // tab[k][g*ld + col], k = (al.hi, al.lo, be.hi, be.lo, ga.hi, ga.lo, mu.hi, mu.lo): fp64 -> float pairs once per
+  // block (not per element); structure-of-arrays so a warp's float4 reads are conflict-free.
+  extern __shared__ __align__(16) float tab[];
+  const long long GC = (long long)G * C;
+  const int GL = G * (int)ld;
+  for (int p = threadIdx.x; p < GL; p += blockDim.x) {
+    const int g = p / (int)ld, col = p - g * (int)ld;
+    F2 al = {0.f, 0.f}, be = al, ga = al, mu = al;
+    if (col < C) {
+      const long long q = (long long)g * C + col;
+      al = split_d(coef[q]); be = split_d(coef[GC + q]); ga = split_d(coef[2 * GC + q]); mu = split_d(mean_rstd[q]);
+    }
+    tab[0 * GL + p] = al.hi; tab[1 * GL + p] = al.lo; tab[2 * GL + p] = be.hi; tab[3 * GL + p] = be.lo;
+    tab[4 * GL + p] = ga.hi; tab[5 * GL + p] = ga.lo; tab[6 * GL + p] = mu.hi; tab[7 * GL + p] = mu.lo;
+  }
+  __syncthreads();
   const long long ld4 = ld >> 2;
   const long long total = (long long)G * R * ld4;
-  const long long GC = (long long)G * C;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     const long long row = t / ld4;
@@ -324,19 +349,23 @@ __global__ void __launch_bounds__(EW_THREADS) affine2_kernel(const float* t1, co
     const int g = (int)(row / R);
     const float4 u = *reinterpret_cast<const float4*>(t1 + t * 4);
     const float4 v = ldg4(t2 + t * 4);
-    const float ui[4] = {u.x, u.y, u.z, u.w}, vi[4] = {v.x, v.y, v.z, v.w};
-    float o[4];
+    const int p = g * (int)ld + c4 * 4;
+    float4 k[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = c4 * 4 + j;
-      if (col < C) {
-        const long long p = (long long)g * C + col;
-        o[j] = (float)(coef[p] * (double)ui[j] + coef[GC + p] * ((double)vi[j] - mean_rstd[p]) + coef[2 * GC + p]);
-      } else {
-        o[j] = 0.f;
-      }
+    for (int i = 0; i < 8; ++i) k[i] = *reinterpret_cast<const float4*>(tab + i * GL + p);
+    float4 o;
+#define SB_AFF2(c)                                                                 \
+    {                                                                              \
+      const float d = (v.c - k[6].c) - k[7].c;      /* t2 - mean */                \
+      float acc = fmaf(k[3].c, d, k[5].c);          /* be.lo * d + ga.lo */        \
+      acc = fmaf(k[1].c, u.c, acc);                 /* + al.lo * t1 */             \
+      acc = fmaf(k[2].c, d, acc + k[4].c);          /* + be.hi * d + ga.hi */      \
+      o.c = fmaf(k[0].c, u.c, acc);                 /* + al.hi * t1 */             \
     }
-    *reinterpret_cast<float4*>(out + t * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    SB_AFF2(x) SB_AFF2(y) SB_AFF2(z) SB_AFF2(w)
+#undef SB_AFF2
+    // padding columns: every table entry is 0 there, so o = 0 as required
+    *reinterpret_cast<float4*>(out + t * 4) = o;
   }
 }
 
@@ -349,7 +378,9 @@ extern "C" int sb_affine2(const float* t1, const float* t2, const double* coef, 
   const long long cap = (long long)sb_num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  affine2_kernel<<<(unsigned)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>(t1, t2, coef, mean_rstd, out, ld, R, G, C);
+  const size_t smem = (size_t)G * ld * 8 * sizeof(float);
+  SB_CHECK_ARG(smem <= 48 * 1024, "sb_affine2: G*ld too large");
+  affine2_kernel<<<(unsigned)blocks, EW_THREADS, smem, (cudaStream_t)stream>>>(t1, t2, coef, mean_rstd, out, ld, R, G, C);
   SB_CHECK_LAUNCH("sb_affine2");
   return SB_OK;
 }

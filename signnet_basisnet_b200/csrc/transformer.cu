@@ -11,37 +11,7 @@
 
 #define ATT_THREADS 128
 
-struct AttArgs {
-  const float* q;
-  const float* k;
-  const float* v;
-  long long ld;      // row stride of q/k/v/o (and their gradients)
-  const int64_t* batch;
-  const int32_t* graph_ptr;
-  const int64_t* row_ptr;
-  long long N;
-  int kslots, masked, n_head, dk;
-  float inv_temp_div;  // temperature (sqrt(dk)); q is divided by it
-  float drop_p;
-  unsigned long long seed;
-  float* o;
-  // backward only
-  const float* go;
-  float* gq;
-  float* gk;
-  float* gv;
-};
-
-__device__ __forceinline__ float att_keep_scale(unsigned long long seed, long long node, int h, int j1, int j2,
-                                                float p) {
-  // counter-based hash (splitmix64) -> uniform in [0,1); the same mask is regenerated in the backward
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(((node * 64 + h) * 4096 + j1) * 4096 + j2 + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
-  return (u >= p) ? 1.0f / (1.0f - p) : 0.0f;
-}
+#include "attention.cuh"
 
 // shared layout helper
 struct AttSmem {
@@ -186,6 +156,10 @@ extern "C" int sb_attention_fwd(const float* q, const float* k, const float* v, 
   a.q = q; a.k = k; a.v = v; a.ld = ld; a.batch = batch; a.graph_ptr = graph_ptr; a.row_ptr = row_ptr; a.N = N;
   a.kslots = kslots; a.masked = masked; a.n_head = n_head; a.dk = dk; a.inv_temp_div = temperature;
   a.drop_p = drop_p; a.seed = (unsigned long long)seed; a.o = o; a.go = nullptr; a.gq = a.gk = a.gv = nullptr;
+  {
+    const int rc = sb_attention_fast_fwd_launch(a, kmax, (cudaStream_t)stream);
+    if (rc != SB_ERR_UNSUPPORTED) return rc;
+  }
   const size_t smem = att_smem(kmax, dk, false);
   SB_CHECK_ARG(smem <= 200 * 1024, "sb_attention_fwd: sequence too long for shared memory (k=%d, dk=%d)", kmax, dk);
   SB_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -206,6 +180,10 @@ extern "C" int sb_attention_bwd(const float* q, const float* k, const float* v, 
   a.q = q; a.k = k; a.v = v; a.ld = ld; a.batch = batch; a.graph_ptr = graph_ptr; a.row_ptr = row_ptr; a.N = N;
   a.kslots = kslots; a.masked = masked; a.n_head = n_head; a.dk = dk; a.inv_temp_div = temperature;
   a.drop_p = drop_p; a.seed = (unsigned long long)seed; a.o = nullptr; a.go = go; a.gq = gq; a.gk = gk; a.gv = gv;
+  {
+    const int rc = sb_attention_fast_bwd_launch(a, kmax, (cudaStream_t)stream);
+    if (rc != SB_ERR_UNSUPPORTED) return rc;
+  }
   const size_t smem = att_smem(kmax, dk, true);
   SB_CHECK_ARG(smem <= 200 * 1024, "sb_attention_bwd: sequence too long for shared memory (k=%d, dk=%d)", kmax, dk);
   SB_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

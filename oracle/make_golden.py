@@ -1,0 +1,114 @@
+"""Generates the committed golden fixtures under tests/golden/ by running the reference's OWN modules (unmodified,
+imported from /root/reference through oracle/ref_loader.py with the stand-in L1 ops of oracle/shim/) on small seeded
+inputs.  TEST INFRASTRUCTURE ONLY.  Run in the authoring container:   python oracle/make_golden.py
+The fixtures travel to the GPU box (where /root/reference does not exist) and pin both the CPU oracle
+(tests/test_oracle_golden.py) and the CUDA path (tests/test_gpu_golden.py)."""
+import copy
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_loader  # noqa: E402
+from signnet_basisnet_b200.synth import synth_batch  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _data_dict(d):
+    return {k: v for k, v in d.__dict__.items() if torch.is_tensor(v) or isinstance(v, int)}
+
+
+def _sd(m):
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def _grads(m):
+    return {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+
+
+def make_alchemy():
+    sn = ref_loader.alchemy()
+    tr = ref_loader.alchemy_transform()
+    torch.manual_seed(0)
+    d = synth_batch(5, "alchemy", seed=41)
+    d.eigen_values = d.eigen_values + 0.02 * torch.randn(d.eigen_values.shape, generator=torch.Generator().manual_seed(9))
+    out = {"data": _data_dict(d)}
+    S, V = tr.to_dense_list_EVD(d.eigen_values, d.eigen_vectors, d.batch)
+    out["dense_list_evd"] = {"eigS": S, "eigV": V}
+    # phi alone (GNN3d), +v and -v passes
+    phi = sn.GNN3d(1, 16, 3)
+    with torch.no_grad():
+        for n_, p in phi.named_parameters():
+            if n_.endswith("bn.weight"):
+                p.uniform_(0.5, 1.5)
+            elif n_.endswith("bn.bias") or n_.endswith("eps"):
+                p.uniform_(-0.3, 0.3)
+    sd0 = _sd(phi)
+    mask = torch.arange(V.shape[1])[None, :] < torch.bincount(d.batch)[d.batch][:, None]
+    x = V.unsqueeze(-1)
+    y = phi(x, d.edge_index, None, mask) + phi(-x, d.edge_index, None, mask)
+    w = torch.randn(y.shape, generator=torch.Generator().manual_seed(1)) * mask.unsqueeze(-1)
+    (y * w).sum().backward()
+    out["phi"] = {"state_dict": sd0, "out": y.detach(), "w": w, "grads": _grads(phi), "state_dict_after": _sd(phi),
+                  "cfg": dict(n_hid=16, n_layer=3)}
+    # full SignNetGNN (attention dropout set to 0: reference quirk, see oracle/restate.py)
+    model = sn.SignNetGNN(6, 4, n_hid=16, n_out=3, nl_signnet=2, nl_gnn=2)
+    for lyr in model.sign_net.rho.transformer_layers:
+        lyr.slf_attn.attention.dropout.p = 0.0
+    sd0 = _sd(model)
+    o = model(copy.copy(d))
+    o.abs().sum().backward()
+    out["signnetgnn"] = {"state_dict": sd0, "out": o.detach(), "grads": _grads(model), "state_dict_after": _sd(model),
+                         "cfg": dict(node_feat=6, edge_feat=4, n_hid=16, n_out=3, nl_signnet=2, nl_gnn=2)}
+    model.eval()
+    out["signnetgnn"]["out_eval"] = model(copy.copy(d)).detach()
+    torch.save(out, os.path.join(OUT, "alchemy_pyg.pt"))
+
+
+def make_dgl():
+    import dgl
+
+    ds, _, _ = ref_loader.graphprediction_layers()
+    torch.manual_seed(1)
+    k = 6
+    d = synth_batch(4, "zinc", seed=42, k_dgl=k)
+    g = dgl.BatchedGraph(d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph)
+    out = {"data": _data_dict(d), "k": k}
+    for name, net in (("gin", ds.GINDeepSigns(1, 12, 4, 4, k, use_bn=True, dropout=0.0, activation="relu")),
+                      ("masked_gin", ds.MaskedGINDeepSigns(1, 12, 12, 4, k, "cpu", use_bn=True, dropout=0.0,
+                                                           activation="relu"))):
+        sd0 = _sd(net)
+        x = d.pos_enc.unsqueeze(-1)
+        y = net(g, x)
+        w = torch.randn(y.shape, generator=torch.Generator().manual_seed(2))
+        (y * w).sum().backward()
+        out[name] = {"state_dict": sd0, "out": y.detach(), "w": w, "grads": _grads(net), "state_dict_after": _sd(net),
+                     "cfg": dict(hidden=12, out=(4 if name == "gin" else 12), layers=4)}
+    torch.save(out, os.path.join(OUT, "dgl_deepsigns.pt"))
+
+
+def make_ign():
+    ign, _ = ref_loader.learningfilters()
+    torch.manual_seed(3)
+    net = ign.IGN2to1(1, 8, 2, device="cpu")
+    V = torch.linalg.qr(torch.randn(20, 6))[0]
+    P = torch.stack([V[:, :2] @ V[:, :2].T, V[:, 2:4] @ V[:, 2:4].T, V[:, 4:6] @ V[:, 4:6].T]).unsqueeze(1)
+    sd0 = _sd(net)
+    y = net(P)
+    torch.save({"state_dict": sd0, "V": V, "P": P, "out": y.detach()}, os.path.join(OUT, "ign2to1.pt"))
+
+
+if __name__ == "__main__":
+    assert ref_loader.available(), "needs the read-only reference mount"
+    os.makedirs(OUT, exist_ok=True)
+    make_alchemy()
+    make_dgl()
+    make_ign()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))

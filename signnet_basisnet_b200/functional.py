@@ -133,43 +133,44 @@ class BatchNormActFn(torch.autograd.Function):
     """out = act(BN(x[:, :C])) (+ res) on [M, ld] rows; nn.BatchNorm1d numerics (biased var, eps 1e-5, momentum .1)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, res, rmean, rvar, training, relu, C):
+    def forward(ctx, x, gamma, beta, res, rmean, rvar, training, relu, C, G=1):
+        """x [M, ld] (G = 1) or [G, M, ld]: statistics are kept per leading group (the two sign passes)."""
         _require_cuda(x, "x")
         x = x.contiguous()
-        M, ld = x.shape
+        M, ld = x.shape[-2], x.shape[-1]
         if ld % 4 != 0:
             raise ValueError("batch_norm_act expects a padded activation (ld % 4 == 0)")
         dev = x.device
         stats = None
         if training:
-            stats = torch.zeros(1, 2, C, dtype=torch.float64, device=dev)
-            _call("sb_col_stats", _p(x), ld, M, 1, C, _p(stats))
-        a, c, mr = bn_finalize(stats, M, 1, C, gamma, beta, rmean, rvar, training, dev)
+            stats = torch.zeros(G, 2, C, dtype=torch.float64, device=dev)
+            _call("sb_col_stats", _p(x), ld, M, G, C, _p(stats))
+        a, c, mr = bn_finalize(stats, M, G, C, gamma, beta, rmean, rvar, training, dev)
         out = torch.empty_like(x)
-        _call("sb_affine_act_res", _p(x), _p(a), _p(c), _p(res), _p(out), ld, M, 1, C, int(relu))
+        _call("sb_affine_act_res", _p(x), _p(a), _p(c), _p(res), _p(out), ld, M, G, C, int(relu))
         ctx.save_for_backward(x, a, c, mr, gamma)
-        ctx.cfg = (training, relu, C, res is not None)
+        ctx.cfg = (training, relu, C, res is not None, G)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         x, a, c, mr, gamma = ctx.saved_tensors
-        training, relu, C, has_res = ctx.cfg
+        training, relu, C, has_res, G = ctx.cfg
         gout = gout.contiguous()
-        M, ld = x.shape
+        M, ld = x.shape[-2], x.shape[-1]
         gx = torch.empty_like(x)
-        dgamma, dbeta = bn_backward(gout, x, a, c, mr, gamma, ld, M, 1, C, relu, training, gx)
-        return gx, dgamma, dbeta, (gout if has_res else None), None, None, None, None, None
+        dgamma, dbeta = bn_backward(gout, x, a, c, mr, gamma, ld, M, G, C, relu, training, gx)
+        return gx, dgamma, dbeta, (gout if has_res else None), None, None, None, None, None, None
 
 
-def batch_norm_act(x, bn: torch.nn.BatchNorm1d, training, relu=True, res=None, C=None):
+def batch_norm_act(x, bn: torch.nn.BatchNorm1d, training, relu=True, res=None, C=None, G=1):
     C = bn.num_features if C is None else C
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+        bn.num_batches_tracked += G
     use_batch = training or not bn.track_running_stats
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
-    return BatchNormActFn.apply(x, bn.weight, bn.bias, res, rm, rv, use_batch, relu, C)
+    return BatchNormActFn.apply(x, bn.weight, bn.bias, res, rm, rv, use_batch, relu, C, G)
 
 
 class SlotSumFn(torch.autograd.Function):

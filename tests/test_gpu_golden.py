@@ -1,0 +1,103 @@
+"""CUDA path against the committed golden fixtures (outputs/gradients of the reference's own modules)."""
+import os
+
+import pytest
+import torch
+
+from helpers import assert_close_rel, assert_grads_close, rows_to_dense, slot_row_index
+from signnet_basisnet_b200.synth import Data
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def test_dense_list_evd_golden_bit_exact(golden_dir):
+    from signnet_basisnet_b200 import ops
+
+    g = _load(golden_dir, "alchemy_pyg.pt")
+    d = Data(**g["data"]).to(DEV)
+    S, V = ops.to_dense_list_EVD(d.eigen_values, d.eigen_vectors, d.batch)
+    assert torch.equal(S.cpu(), g["dense_list_evd"]["eigS"]) and torch.equal(V.cpu(), g["dense_list_evd"]["eigV"])
+
+
+def test_phi_golden(golden_dir):
+    from signnet_basisnet_b200.layout import GraphIndex, pad4
+    from signnet_basisnet_b200.sign_net import GNN3d, build_phi_input
+
+    g = _load(golden_dir, "alchemy_pyg.pt")
+    d, ph = Data(**g["data"]), g["phi"]
+    nh, nl = ph["cfg"]["n_hid"], ph["cfg"]["n_layer"]
+    phi = GNN3d(1, nh, nl).to(DEV).train()
+    phi.load_state_dict(ph["state_dict"])
+    dd = d.to(DEV)
+    gi = GraphIndex(dd.edge_index, dd.batch, d.num_graphs)
+    sl = gi.slots_all(pad4(nh))
+    x0 = build_phi_input(gi, sl, dd.eigen_vectors)
+    xr, sl = phi.forward_rows(x0, gi, sl.k, True)
+    idx = slot_row_index(d.batch, sl.k, True)
+    got = rows_to_dense(xr[0].cpu(), idx, nh) + rows_to_dense(xr[1].cpu(), idx, nh)
+    assert_close_rel(got, ph["out"], 1e-5, what="phi vs reference")
+    for k, v in ph["state_dict_after"].items():
+        if "num_batches" in k:
+            assert torch.equal(phi.state_dict()[k].cpu(), v), k
+
+
+def test_signnetgnn_golden(golden_dir):
+    from signnet_basisnet_b200.sign_net import SignNetGNN
+
+    g = _load(golden_dir, "alchemy_pyg.pt")
+    d, m = Data(**g["data"]), g["signnetgnn"]
+    c = m["cfg"]
+    model = SignNetGNN(c["node_feat"], c["edge_feat"], c["n_hid"], c["n_out"], c["nl_signnet"], c["nl_gnn"]).to(DEV)
+    model.load_state_dict(m["state_dict"])  # a reference checkpoint loads unchanged
+    for lyr in model.sign_net.rho.transformer_layers:
+        lyr.slf_attn.attention.dropout.p = 0.0
+    model.train()
+    out = model(d.to(DEV))
+    assert_close_rel(out.cpu(), m["out"], 1e-5, what="SignNetGNN vs reference (train)")
+    out.abs().sum().backward()
+    got = {k: p.grad.cpu() for k, p in model.named_parameters() if p.grad is not None}
+    assert_grads_close(got, m["grads"], 5e-5, "SignNetGNN vs reference")
+    model.eval()
+    with torch.no_grad():
+        out_e = model(d.to(DEV))
+    assert_close_rel(out_e.cpu(), m["out_eval"], 2e-5, what="SignNetGNN vs reference (eval)")
+
+
+class _G:
+    def __init__(self, d):
+        self.src, self.dst, self.n = d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph
+
+    def edges(self):
+        return self.src, self.dst
+
+    def batch_num_nodes(self):
+        return self.n
+
+
+@pytest.mark.parametrize("name", ["gin", "masked_gin"])
+def test_dgl_deepsigns_golden(golden_dir, name):
+    from signnet_basisnet_b200.deepsigns import get_sign_inv_net
+
+    g = _load(golden_dir, "dgl_deepsigns.pt")
+    d, m, k = Data(**g["data"]).to(DEV), g[name], g["k"]
+    net = get_sign_inv_net(dict(sign_inv_net=name, hidden_dim=m["cfg"]["hidden"], phi_out_dim=m["cfg"]["out"],
+                                sign_inv_layers=m["cfg"]["layers"], pos_enc_dim=k, dropout=0.0,
+                                sign_inv_activation="relu", device=DEV)).to(DEV).train()
+    assert set(net.state_dict()) == set(m["state_dict"])
+    net.load_state_dict(m["state_dict"])
+    out = net(_G(d), d.pos_enc.unsqueeze(-1))
+    assert out.shape == m["out"].shape
+    assert_close_rel(out.cpu(), m["out"], 2e-5, what=f"{name} vs reference")
+    (out * m["w"].to(DEV)).sum().backward()
+    got = {k_: p.grad.cpu() for k_, p in net.named_parameters() if p.grad is not None}
+    assert_grads_close(got, m["grads"], 1e-4, f"{name} vs reference")
+    for k_, v in m["state_dict_after"].items():
+        if "running_" in k_:
+            assert_close_rel(net.state_dict()[k_].cpu(), v, 2e-5, what=k_)
+        elif "num_batches" in k_:
+            assert torch.equal(net.state_dict()[k_].cpu(), v), k_

@@ -1,0 +1,82 @@
+"""CPU oracle (oracle/restate.py) against the committed golden fixtures, which were produced by the reference's own
+modules (oracle/make_golden.py).  Runs everywhere, including the GPU box where /root/reference is absent."""
+import os
+
+import pytest
+import torch
+
+import restate
+from helpers import assert_close_rel, assert_grads_close
+from signnet_basisnet_b200.synth import Data
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _leaf(sd):
+    sd = {k: v.clone() for k, v in sd.items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    return sd
+
+
+def test_dense_list_evd_golden(golden_dir):
+    g = _load(golden_dir, "alchemy_pyg.pt")
+    d = Data(**g["data"])
+    S, V = restate.dense_list_evd(d.eigen_values, d.eigen_vectors, d.batch)
+    assert torch.equal(S, g["dense_list_evd"]["eigS"]) and torch.equal(V, g["dense_list_evd"]["eigV"])
+
+
+def test_phi_golden(golden_dir):
+    g = _load(golden_dir, "alchemy_pyg.pt")
+    d, ph = Data(**g["data"]), g["phi"]
+    sd = _leaf(ph["state_dict"])
+    V = g["dense_list_evd"]["eigV"]
+    mask = restate.slot_mask(d.batch, V.shape[1])
+    out = restate.phi_pm(V, d.edge_index, mask, sd, "", ph["cfg"]["n_layer"], True)
+    assert_close_rel(out, ph["out"], 1e-6, what="phi")
+    (out * ph["w"]).sum().backward()
+    assert_grads_close({k: v.grad for k, v in sd.items()}, ph["grads"], 1e-5, "phi")
+    for k, v in ph["state_dict_after"].items():
+        if "running_" in k:
+            assert_close_rel(sd[k], v, 1e-6, what=k)
+        elif "num_batches" in k:
+            assert torch.equal(sd[k], v), k
+
+
+def test_signnetgnn_golden(golden_dir):
+    g = _load(golden_dir, "alchemy_pyg.pt")
+    d, m = Data(**g["data"]), g["signnetgnn"]
+    sd = _leaf(m["state_dict"])
+    out = restate.sign_net_gnn(d, sd, m["cfg"]["nl_signnet"], m["cfg"]["nl_gnn"])
+    assert_close_rel(out, m["out"], 1e-5, what="SignNetGNN")
+    out.abs().sum().backward()
+    assert_grads_close({k: v.grad for k, v in sd.items()}, m["grads"], 2e-5, "SignNetGNN")
+    sd_eval = {k: v.clone() for k, v in m["state_dict_after"].items()}
+    with torch.no_grad():
+        out_e = restate.sign_net_gnn(d, sd_eval, m["cfg"]["nl_signnet"], m["cfg"]["nl_gnn"], training=False)
+    assert_close_rel(out_e, m["out_eval"], 1e-5, what="SignNetGNN eval")
+
+
+@pytest.mark.parametrize("name", ["gin", "masked_gin"])
+def test_dgl_deepsigns_golden(golden_dir, name):
+    g = _load(golden_dir, "dgl_deepsigns.pt")
+    d, m, k = Data(**g["data"]), g[name], g["k"]
+    sd = _leaf(m["state_dict"])
+    x = d.pos_enc.unsqueeze(-1)
+    if name == "gin":
+        out = restate.gin_deepsigns(x, d.edge_index[0], d.edge_index[1], sd, m["cfg"]["layers"], k)
+    else:
+        out = restate.masked_gin_deepsigns(x, d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph, sd,
+                                           m["cfg"]["layers"], k)
+    assert_close_rel(out, m["out"], 2e-5, what=name)
+    (out * m["w"]).sum().backward()
+    assert_grads_close({k_: v.grad for k_, v in sd.items()}, m["grads"], 5e-5, name)
+
+
+def test_ign2to1_golden(golden_dir):
+    g = _load(golden_dir, "ign2to1.pt")
+    sd = {k: v.clone() for k, v in g["state_dict"].items()}
+    assert_close_rel(restate.ign2to1(g["P"], sd), g["out"], 1e-5, what="IGN2to1")

@@ -51,6 +51,16 @@ int sb_slot_layout(const int32_t* graph_ptr, int32_t B, int32_t k, int32_t maske
                    int64_t* row_ptr, int64_t* vec_ptr, int32_t* unit_ptr, int64_t* summary, void* stream);
 int sb_agg_units(const int32_t* graph_ptr, int32_t B, int32_t k, int32_t masked, int32_t tile_rows,
                  int32_t* unit_ptr, void* stream);
+/* unit_desc[U][12] int32: one record per aggregate work unit = (graph, slot chunk) tile of <= tile_rows rows:
+ * {row_rel lo, hi, n_b, rows, node0, ceil(2^32/n_b), first edge / edge count of the graph in the CSR by destination,
+ * the same for the CSR by source, 0, 0}.  cap_units = records allocated (U <= N if masked else B*k). */
+/* nbr_pack[N]: per node, up to four local neighbour ids (id - first node of its graph) of one CSR, a byte each in
+ * CSR order, 0xFF = empty; 0xFE in byte 3 = degree > 4 or id > 253 (the aggregate walks the CSR for that node). */
+int sb_pack_neighbours(const int64_t* batch, const int32_t* graph_ptr, const int32_t* nbr_ptr, const int32_t* nbr_idx,
+                       int64_t N, uint32_t* nbr_pack, void* stream);
+int sb_agg_unit_desc(const int32_t* graph_ptr, const int64_t* row_ptr, const int32_t* unit_ptr, const int32_t* in_ptr,
+                     const int32_t* out_ptr, int32_t B, int32_t k, int32_t masked, int32_t tile_rows,
+                     int32_t* unit_desc, int64_t cap_units, void* stream);
 
 /* Stable CSR by destination (in_*) and by source (out_*) of edge_index[2,E]; rows keep edge-id order so neighbour
  * sums accumulate in the order torch's CPU index_add_ uses.  workspace: >= 2*(N+1) + 2*ceil((N+1)/4096) int32.
@@ -88,12 +98,13 @@ int sb_dense_to_rows(const float* dense, int64_t R, int32_t S, int32_t negate_se
 
 /* ---- K1: GIN neighbourhood aggregate ------------------------------------------------------------------------------
  * out = [res +] (1+eps)*x + sum_{nbr} x   on [S, R, ld] slot rows; (nbr_ptr, nbr_idx) = CSR by destination for the
- * forward, by source for the backward.  Optional dot_out += sum(x * dotx) (= d eps in the backward).
+ * forward, by source for the backward; nbr_pack = the packed neighbour words of the SAME CSR (sb_pack_neighbours);
+ * unit_desc or nbr_pack NULL => generic kernel.  Optional dot_out += sum(x * dotx) (= d eps in the backward).
  * Replaces gnn.GINConv(Identity(), train_eps=True) (masked_layers.py:70,75) / dgl GINConv(.,'sum') (gnns.py:90-98). */
 int sb_gin_agg(const float* x, float* out, const float* res, const float* dotx, double* dot_out, const float* eps,
-               const int32_t* graph_ptr, const int32_t* unit_ptr, const int64_t* row_ptr, const int32_t* nbr_ptr,
-               const int32_t* nbr_idx, int64_t R, int32_t B, int32_t k, int32_t masked, int32_t S, int32_t ld,
-               int32_t tile_rows, int32_t force_generic, void* stream);
+               const int32_t* graph_ptr, const int32_t* unit_ptr, const int32_t* unit_desc, const uint32_t* nbr_pack,
+               const int64_t* row_ptr, const int32_t* nbr_ptr, const int32_t* nbr_idx, int64_t R, int32_t B, int32_t k,
+               int32_t masked, int32_t S, int32_t ld, int32_t tile_rows, int32_t force_generic, void* stream);
 int sb_gin_agg_tile_rows(int32_t ld); /* rows per shared-memory tile of the TMA path (0 = generic path only) */
 
 /* ---- K2: Linear with fused BatchNorm prologue / statistics epilogue ------------------------------------------------

@@ -24,7 +24,9 @@ _SIGNATURES = {
     "sb_dense_list_evd": "ppppp" + "li" + "ppp" + "p",
     "sb_rows_to_dense": "pll" + "i" + "ppp" + "l" + "iii" + "p" + "p",
     "sb_dense_to_rows": "pl" + "ii" + "ppp" + "l" + "iii" + "l" + "p" + "p",
-    "sb_gin_agg": "ppppp" + "p" + "ppppp" + "l" + "iiiiiii" + "p",
+    "sb_agg_unit_desc": "ppppp" + "iiii" + "pl" + "p",
+    "sb_pack_neighbours": "pppp" + "l" + "p" + "p",
+    "sb_gin_agg": "ppppp" + "p" + "ppppppp" + "l" + "iiiiiii" + "p",
     "sb_linear_fwd": "pl" + "pll" + "p" + "pl" + "l" + "iii" + "ipp" + "i" + "p" + "i" + "p",
     "sb_linear_wgrad": "pl" + "pl" + "l" + "iii" + "ipp" + "pll" + "p" + "i" + "p" + "p",
     "sb_col_stats": "pll" + "ii" + "p" + "p",
@@ -123,8 +125,8 @@ def counted_call(name, *args):
 
 
 def _profile_tag(name, args):
-    if name == "sb_gin_agg":  # (.., R, B, k, masked, S, ld, tile_rows, force_generic): split by row width / path
-        return f"sb_gin_agg[ld={args[16]}{',generic' if args[18] else ''}{',bwd' if args[2] or args[3] else ''}]"
+    if name == "sb_gin_agg":  # (.. 13 pointers, R, B, k, masked, S, ld, tile_rows, force_generic): split by row width / path
+        return f"sb_gin_agg[ld={args[18]}{',generic' if args[20] else ''}{',bwd' if args[2] or args[3] else ''}]"
     if name == "sb_linear_fwd":    # (x, ldx, w, rs, cs, bias, y, ldy, R, G, K, N, pro, ...)
         return f"sb_linear_fwd[K={args[10]},N={args[11]},rows={args[8] * args[9]}]"
     if name == "sb_linear_wgrad":  # (gy, ldg, x, ldx, R, G, N, K, ...)

@@ -195,6 +195,87 @@ extern "C" int sb_agg_units(const int32_t* graph_ptr, int32_t B, int32_t k, int3
   return SB_OK;
 }
 
+// Descriptor table of the aggregate's work units (one 48-byte record per (graph, slot-chunk) tile), so the producer
+// warp of gin_agg_tma_kernel finds a tile with ONE coalesced load instead of a binary search + dependent pointer chase.
+//   int32[12] = { row_rel lo, row_rel hi, n, rows, node0, magic = ceil(2^32/n), e0_in, ne_in, e0_out, ne_out, 0, 0 }
+__global__ void agg_unit_desc_kernel(const int32_t* __restrict__ gp, const int64_t* __restrict__ row_ptr,
+                                     const int32_t* __restrict__ unit_ptr, const int32_t* __restrict__ in_ptr,
+                                     const int32_t* __restrict__ out_ptr, int B, int k, int masked, int tile_rows,
+                                     int32_t* __restrict__ desc, long long cap) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int node0 = gp[b];
+  const int n = gp[b + 1] - node0;
+  if (n <= 0) return;
+  const int kb = masked ? (n < k ? n : k) : k;
+  int G = tile_rows / n;
+  if (G < 1) G = 1;
+  const int u0 = unit_ptr[b], u1 = unit_ptr[b + 1];
+  const long long r0 = row_ptr[b];
+  const int e0i = in_ptr[node0], nei = in_ptr[node0 + n] - e0i;
+  const int e0o = out_ptr[node0], neo = out_ptr[node0 + n] - e0o;
+  const unsigned magic = (unsigned)((0x100000000ull + (unsigned)n - 1) / (unsigned)n);
+  for (int u = u0; u < u1 && u < cap; ++u) {
+    const int j0 = (u - u0) * G;
+    const int ns = (kb - j0 < G) ? (kb - j0) : G;
+    const long long rr = r0 + (long long)j0 * n;
+    int32_t* d = desc + (long long)u * 12;
+    d[0] = (int32_t)(rr & 0xffffffffll);
+    d[1] = (int32_t)(rr >> 32);
+    d[2] = n;
+    d[3] = ns * n;
+    d[4] = node0;
+    d[5] = (int32_t)magic;
+    d[6] = e0i; d[7] = nei; d[8] = e0o; d[9] = neo;
+    d[10] = 0; d[11] = 0;
+  }
+}
+
+extern "C" int sb_agg_unit_desc(const int32_t* graph_ptr, const int64_t* row_ptr, const int32_t* unit_ptr,
+                                const int32_t* in_ptr, const int32_t* out_ptr, int32_t B, int32_t k, int32_t masked,
+                                int32_t tile_rows, int32_t* unit_desc, int64_t cap_units, void* stream) {
+  SB_CHECK_ARG(B >= 0 && k >= 1 && tile_rows >= 1 && cap_units >= 0, "sb_agg_unit_desc: bad args");
+  if (B == 0) return SB_OK;
+  agg_unit_desc_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(graph_ptr, row_ptr, unit_ptr, in_ptr,
+                                                                          out_ptr, B, k, masked, tile_rows, unit_desc,
+                                                                          cap_units);
+  SB_CHECK_LAUNCH("sb_agg_unit_desc");
+  return SB_OK;
+}
+
+// Packed neighbour word per node for the TMA aggregate: up to four LOCAL neighbour ids (node id - first node of the
+// graph) in CSR order, one per byte, 0xFF = empty.  Byte 3 = 0xFE marks a node the fast path cannot express (degree
+// > 4 or a local id > 253): the aggregate then walks the CSR for that node.
+__global__ void pack_neighbours_kernel(const int64_t* __restrict__ batch, const int32_t* __restrict__ gp,
+                                       const int32_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr_idx,
+                                       long long N, uint32_t* __restrict__ pack) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int node0 = gp[batch[i]];
+  const int beg = nbr_ptr[i], end = nbr_ptr[i + 1];
+  uint32_t w = 0xFFFFFFFFu;
+  bool slow = end - beg > 4;
+  if (!slow) {
+    for (int e = beg; e < end; ++e) {
+      const int lj = nbr_idx[e] - node0;
+      if (lj < 0 || lj > 253) { slow = true; break; }
+      const int q = e - beg;
+      w = (w & ~(0xFFu << (8 * q))) | ((uint32_t)lj << (8 * q));
+    }
+  }
+  pack[i] = slow ? 0xFEFFFFFFu : w;
+}
+
+extern "C" int sb_pack_neighbours(const int64_t* batch, const int32_t* graph_ptr, const int32_t* nbr_ptr,
+                                  const int32_t* nbr_idx, int64_t N, uint32_t* nbr_pack, void* stream) {
+  SB_CHECK_ARG(N >= 0, "sb_pack_neighbours: bad N");
+  if (N == 0) return SB_OK;
+  pack_neighbours_kernel<<<(unsigned)sb_ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(batch, graph_ptr, nbr_ptr,
+                                                                                          nbr_idx, N, nbr_pack);
+  SB_CHECK_LAUNCH("sb_pack_neighbours");
+  return SB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------ device scan
 // exclusive scan of int32 counts (n elements, in place), n <= 4096*4096.
 #define SCAN_ITEMS 4

@@ -60,6 +60,13 @@ class GraphIndex:
         ws = torch.empty(ws_ints, **i32)
         _call("sb_build_csr", _p(self.edge_index), E, N, _p(self.batch), _p(self.in_ptr), _p(self.in_src),
               _p(self.in_eid), _p(self.out_ptr), _p(self.out_dst), _p(self.out_eid), _p(ws), ws_ints, _p(self.flags))
+        # packed neighbour words of both CSRs for the TMA aggregate (4 local ids per node in one int32)
+        self.in_pack = torch.empty(max(N, 1), **i32)
+        self.out_pack = torch.empty(max(N, 1), **i32)
+        _call("sb_pack_neighbours", _p(self.batch), _p(self.graph_ptr), _p(self.in_ptr), _p(self.in_src), N,
+              _p(self.in_pack))
+        _call("sb_pack_neighbours", _p(self.batch), _p(self.graph_ptr), _p(self.out_ptr), _p(self.out_dst), N,
+              _p(self.out_pack))
         self._allow_cross = allow_cross_graph
         self._checked = False
         self._slots = {}
@@ -110,6 +117,7 @@ class SlotLayout:
             self.R, self.nmax, self.kmax, self.vec_total = base.R, base.nmax, base.kmax, base.vec_total
             _call("sb_agg_units", _p(gi.graph_ptr), B, k, int(masked), max(tile_rows, 1), _p(self.unit_ptr))
             self.oversize = 0 if (tile_rows >= self.nmax and tile_rows > 0) else 1
+            self._unit_desc()
             return
         self.row_ptr = torch.empty(B + 1, dtype=torch.int64, device=dev)
         self.vec_ptr = torch.empty(B + 1, dtype=torch.int64, device=dev)
@@ -120,6 +128,15 @@ class SlotLayout:
         gi.check(host[8])
         self.R, self.nmax, self.kmax, self.vec_total = (int(host[i]) for i in range(4))
         self.oversize = int(host[5]) if tile_rows > 0 else 1
+        self._unit_desc()
+
+    def _unit_desc(self):
+        """One 48-byte record per aggregate tile (sb_agg_unit_desc); #tiles <= N (masked: k_b <= n_b) or B*k."""
+        gi = self.gi
+        cap = max(1, min(self.R, gi.N if self.masked else gi.B * self.k))
+        self.unit_desc = torch.empty(cap, 12, dtype=torch.int32, device=gi.device)
+        _call("sb_agg_unit_desc", _p(gi.graph_ptr), _p(self.row_ptr), _p(self.unit_ptr), _p(gi.in_ptr), _p(gi.out_ptr),
+              gi.B, self.k, int(self.masked), max(self.tile_rows, 1), _p(self.unit_desc), cap)
 
     @property
     def use_generic_agg(self) -> bool:

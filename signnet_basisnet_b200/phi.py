@@ -28,11 +28,11 @@ PARAMS_PER_LAYER = 8  # W0, bn0.weight, bn0.bias, W1, b1 (or None), eps, bn.weig
 def gin_agg(x, out, slots, S, ld, eps=None, res=None, dotx=None, dot_out=None, transpose=False,
             force_generic=False):
     gi = slots.gi
-    nbr_ptr, nbr_idx = (gi.out_ptr, gi.out_dst) if transpose else (gi.in_ptr, gi.in_src)
+    nbr_ptr, nbr_idx, pack = (gi.out_ptr, gi.out_dst, gi.out_pack) if transpose else (gi.in_ptr, gi.in_src, gi.in_pack)
     generic = force_generic or slots.use_generic_agg or ld % 4 != 0
     _call("sb_gin_agg", _p(x), _p(out), _p(res), _p(dotx), _p(dot_out), _p(eps), _p(gi.graph_ptr),
-          _p(slots.unit_ptr), _p(slots.row_ptr), _p(nbr_ptr), _p(nbr_idx), slots.R, gi.B, slots.k, int(slots.masked),
-          S, ld, max(slots.tile_rows, 1), int(generic))
+          _p(slots.unit_ptr), _p(slots.unit_desc), _p(pack), _p(slots.row_ptr), _p(nbr_ptr), _p(nbr_idx), slots.R, gi.B,
+          slots.k, int(slots.masked), S, ld, max(slots.tile_rows, 1), int(generic))
 
 
 class PhiStackFn(torch.autograd.Function):

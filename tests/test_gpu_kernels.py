@@ -120,6 +120,41 @@ def test_gin_aggregate_bit_exact(C, k, masked, generic):
         assert out[..., C:].abs().max() == 0
 
 
+@pytest.mark.parametrize("C,k,masked", [(128, 37, True), (64, 16, True), (96, 8, False), (20, 6, True)])
+def test_gin_aggregate_backward_mode(C, k, masked):
+    """Backward use of K1: out = res + agg^T(x) with `res` aliasing `out`, plus the d-eps dot product sum(x * dotx)."""
+    from signnet_basisnet_b200.layout import pad4
+    from signnet_basisnet_b200.phi import gin_agg
+
+    d = synth_batch(40, "zinc", seed=9)
+    keep = torch.rand(d.edge_index.shape[1], generator=torch.Generator().manual_seed(3)) < 0.8
+    d.edge_index = d.edge_index[:, keep]
+    idx, xd = _agg_case(d, k, masked, C)
+    _, gd = _agg_case(d, k, masked, C)
+    g = torch.Generator().manual_seed(11)
+    gd = torch.randn(xd.shape, generator=g) * (idx >= 0).unsqueeze(-1)
+    td = torch.randn(xd.shape, generator=g) * (idx >= 0).unsqueeze(-1)
+    eps = torch.tensor([-0.21])
+    flipped = d.edge_index.flip(0)  # transpose of the adjacency: aggregate by source
+    ref = torch.stack([gd[s] + restate.gin_aggregate(xd[s].transpose(0, 1), flipped, eps).transpose(0, 1) for s in (0, 1)])
+    ref_dot = float((xd.double() * td.double()).sum())
+    ld = pad4(C)
+    gi = _gi(d)
+    sl = gi.slots(k, masked, ld)
+    to_rows = lambda t: torch.stack([dense_to_rows(t[s], idx, ld) for s in (0, 1)]).to(DEV)
+    x, G, t = to_rows(xd), to_rows(gd), to_rows(td)
+    for generic in (False, True):
+        out = G.clone()
+        dot = torch.zeros(1, dtype=torch.float64, device=DEV)
+        gin_agg(x, out, sl, 2, ld, eps=eps.to(DEV), res=out, dotx=t, dot_out=dot, transpose=True, force_generic=generic)
+        o = out.cpu()
+        for s in (0, 1):
+            got = rows_to_dense(o[s], idx, C)
+            want = ref[s] * (idx >= 0).unsqueeze(-1)
+            assert (got - want).abs().max() <= 1e-6 * want.abs().max(), f"generic={generic} sign {s}"
+        assert abs(float(dot) - ref_dot) <= 1e-5 * max(1.0, abs(ref_dot)), (generic, float(dot), ref_dot)
+
+
 @pytest.mark.parametrize("K,N,pro,relu,bias", [(128, 128, 0, False, False), (128, 128, 2, False, True),
                                                (64, 64, 2, False, True), (95, 95, 1, True, True),
                                                (1, 64, 0, False, False), (1, 1, 0, False, False),

@@ -5,14 +5,19 @@
 // a single-pass TF32/bf16 product.  Same contract as linear_fwd_kernel (linear.cu): prologue none | BN-affine |
 // BN-affine+ReLU applied once per element, epilogue bias / ReLU / per-(group, channel) fp64 column sums.
 //
-// One persistent CTA per SM, warp-specialised:
-//   warps 0..15  workers: whole-tile register prefetch of the NEXT 128-row tile (64 KB of HBM reads in flight per SM),
-//                prologue + head/tail split + swizzled st.shared of one 32-float K-block at a time into a 2-stage ring,
-//                then the epilogue: tcgen05.ld (one 32x32 block per warp) -> bias/ReLU -> shared staging (the idle
-//                ring) -> coalesced 128-bit stores + fp64 column sums for the BatchNorm that follows;
+// One persistent CTA per SM, three warp roles running concurrently (no block-wide barrier inside the tile loop):
+//   warps 0..7   producers: stream the input as [128 rows x 32 floats] K-blocks (register prefetch two K-blocks ahead,
+//                bulk L2 prefetch three tiles ahead), apply the prologue, split head/tail and st.shared them swizzled
+//                into a 2-stage operand ring; each warp arrives on full[stage] on its own.
 //   warp 16      MMA issuer: waits full[stage], issues 12 x UMMA 128 x N x 8 (kind::tf32) per K-block against the
-//                resident weight (head and tail, canonical K-major SWIZZLE_128B, 128 KB), tcgen05.commit recycles the
-//                ring stage (mma_done) and publishes the accumulator (acc_done).
+//                resident weight (head and tail, canonical K-major SWIZZLE_128B, 128 KB); tcgen05.commit recycles the
+//                ring stage (mma_done) and publishes the accumulator (acc_done).  Two accumulators in tensor memory
+//                alternate, so the MMAs of tile i+1 run while tile i is drained (acc_free hands a buffer back).
+//   warps 8..15  epilogue: tcgen05.ld of a [32 lanes x 32 columns] block (two per warp and tile) -> bias/ReLU ->
+//                per-warp XOR-swizzled shared tile -> 128-bit stores of whole 128-byte row segments + per-column
+//                BatchNorm partial sums (fp32 over the block's 32 rows, fp64 across tiles, one atomic per kernel).
+// The first version ran split -> MMA -> staged epilogue one after the other on the same 16 warps behind bar.syncs and
+// sat at 24 % of DRAM bandwidth with the tensor pipe 19 % busy (profiles/r1g_linear_tc_ncu.csv).
 #include "common.cuh"
 #include "../../include/signnet_b200.h"
 
@@ -20,8 +25,11 @@
 #define TC_KB 32                      // floats per K-block = one 128-byte swizzle row
 #define TC_BLK_BYTES (128 * 128)      // one [128 rows x 32 floats] operand block
 #define TC_WORKERS 512
+#define TC_PROD 256                    // producer threads (warps 0..7); warps 8..15 are the epilogue
 #define TC_THREADS (TC_WORKERS + 32)
 #define TC_MAXG 2
+#define TC_ESTAGE_BYTES (8 * 32 * 32 * 4)    // per-epilogue-warp [32 rows][32 cols] fp32 transposition tile
+#define TC_L2_AHEAD 3   // tiles requested into L2 ahead of the one-tile register prefetch
 
 struct TcArgs {
   const float* x;
@@ -82,16 +90,33 @@ __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" :
                  "=r"(v[30]), "=r"(v[31])                                                                            \
                : "r"(taddr))
 
+// Column sums over the 32 lanes of a warp: lane l ends up with sum_lanes v[l] (a transposing butterfly, 31 shuffles).
+__device__ __forceinline__ float tc_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? v[i] : v[i + h];
+      const float keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0];
+}
+
+// FAST: K and N multiples of 32, 16-byte aligned rows on both sides, ycols == N, no accumulate -> every per-element
+// bounds / alignment predicate of the generic path disappears at compile time (it was ~60 % of the issued instructions).
+template <bool FAST>
 __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nkb = a.nkb;
   uint8_t* Wh = smem;                              // [nkb][16 KB]
   uint8_t* Wl = Wh + nkb * TC_BLK_BYTES;
-  uint8_t* ring = Wl + nkb * TC_BLK_BYTES;         // 2 stages x (head 16 KB | tail 16 KB) = 64 KB; reused as the
-                                                   // [128][128] fp32 staging tile of the epilogue
-  __shared__ double sacc[TC_MAXG * 2 * 128];
-  __shared__ float s_pa[TC_MAXG * 128], s_pc[TC_MAXG * 128], s_bias[128];
-  __shared__ uint64_t full[2], mma_done[2], acc_done;
+  uint8_t* ring = Wl + nkb * TC_BLK_BYTES;         // 2 stages x (head 16 KB | tail 16 KB) = 64 KB
+  float* estage = reinterpret_cast<float*>(ring + 4 * TC_BLK_BYTES);   // [8 warps][32 rows][32 cols] epilogue staging
+  __shared__ __align__(16) float s_pa[TC_MAXG * 128], s_pc[TC_MAXG * 128], s_bias[128];
+  __shared__ uint64_t full[2], mma_done[2], acc_done[2], acc_free[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -117,17 +142,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
     s_pc[idx] = ok ? __ldg(a.pc + (long long)g * K + c) : 0.f;
   }
   for (int idx = tid; idx < 128; idx += TC_THREADS) s_bias[idx] = (a.bias && idx < N) ? __ldg(a.bias + idx) : 0.f;
-  for (int idx = tid; idx < TC_MAXG * 2 * 128; idx += TC_THREADS) sacc[idx] = 0.0;
   if (tid == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
-    mbar_init(&mma_done[0], 1);
-    mbar_init(&mma_done[1], 1);
-    mbar_init(&acc_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], TC_PROD / 32);          // one arrival per producer warp
+      mbar_init(&mma_done[i], 1);
+      mbar_init(&acc_done[i], 1);
+      mbar_init(&acc_free[i], (TC_WORKERS - TC_PROD) / 32);   // one arrival per epilogue warp
+    }
     mbar_fence_init();
   }
   if (warp == 16) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -144,8 +169,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
     if (lane == 0) {
       const uint32_t idesc =
           (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.NP >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      unsigned cnt = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      unsigned cnt = 0, ti = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+        const uint32_t buf = ti & 1u;
+        if (ti >= 2) {   // the workers have drained the accumulator this tile reuses
+          mbar_wait(&acc_free[buf], ((ti >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t tacc = tmem + buf * 128u;
         for (int kb = 0; kb < nkb; ++kb, ++cnt) {
           const int stage = cnt & 1;
           mbar_wait(&full[stage], (cnt >> 1) & 1);
@@ -155,70 +186,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t o = j * 32;
-            tc_mma(tmem, tc_make_desc(ah + o), tc_make_desc(wh + o), idesc, (kb | j) ? 1u : 0u);
-            tc_mma(tmem, tc_make_desc(ah + o), tc_make_desc(wl + o), idesc, 1u);
-            tc_mma(tmem, tc_make_desc(al + o), tc_make_desc(wh + o), idesc, 1u);
+            tc_mma(tacc, tc_make_desc(ah + o), tc_make_desc(wh + o), idesc, (kb | j) ? 1u : 0u);
+            tc_mma(tacc, tc_make_desc(ah + o), tc_make_desc(wl + o), idesc, 1u);
+            tc_mma(tacc, tc_make_desc(al + o), tc_make_desc(wh + o), idesc, 1u);
           }
           tc_commit(&mma_done[stage]);
-          if (kb == nkb - 1) tc_commit(&acc_done);
+          if (kb == nkb - 1) tc_commit(&acc_done[buf]);
         }
       }
     }
-  } else {
-    // ================================================================================================== workers
-    // Whole-tile register prefetch (raw loads only: nothing here may depend on the loaded values).
-    float4 pre[8];
-    auto load_tile = [&](long long tile) {
-      const int g = (int)(tile / tpg);
-      const long long row0 = (tile - (long long)g * tpg) * TC_BM;
-      const int rows = (int)((a.R - row0 < TC_BM) ? (a.R - row0) : TC_BM);
-      const long long base = (long long)g * a.R + row0;
-#pragma unroll
-      for (int kb = 0; kb < 4; ++kb) {
-        if (kb >= nkb) break;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int f = tid + TC_WORKERS * q;
-          const int row = f >> 3, c4 = f & 7;
-          const int col = kb * TC_KB + c4 * 4;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < rows && col < K) {
-            const float* p = a.x + (base + row) * a.ldx + col;
-            if (a.xvec) {
-              v = ldg4(p);
-            } else {
-              v.x = __ldg(p);
-              if (col + 1 < K) v.y = __ldg(p + 1);
-              if (col + 2 < K) v.z = __ldg(p + 2);
-              if (col + 3 < K) v.w = __ldg(p + 3);
-            }
-          }
-          pre[kb * 2 + q] = v;
-        }
-      }
+  } else if (warp < TC_PROD / 32) {
+    // ================================================================================================ producers
+    // thread -> float4 column c4 of rows (tid >> 3) + 32 q, q < 4, of every K-block
+    const int prow = tid >> 3, c4 = tid & 7;
+    float4 pre[2][4];                                  // two K-blocks in flight (slot = position parity)
+    struct Cur { long long tile; int kb; };
+    auto advance = [&](Cur& c) {
+      if (++c.kb == nkb) { c.kb = 0; c.tile += gridDim.x; }
     };
-    // prologue (BatchNorm affine / ReLU) + zeroing of the K tail + head/tail split, applied when a block is consumed
-    auto store_block = [&](int stage, int kb, int g, int rows) {
+#define TC_LOAD_BLOCK(CUR, SLOT)                                                                    \
+    if ((CUR).tile < ntiles) {                                                                      \
+      const int g_ = (int)((CUR).tile / tpg);                                                       \
+      const long long row0_ = ((CUR).tile - (long long)g_ * tpg) * TC_BM;                           \
+      const int rows_ = (int)((a.R - row0_ < TC_BM) ? (a.R - row0_) : TC_BM);                       \
+      const long long base_ = (long long)g_ * a.R + row0_;                                          \
+      const int col_ = (CUR).kb * TC_KB + c4 * 4;                                                   \
+      _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                               \
+        const int row_ = prow + 32 * q;                                                             \
+        float4 v_ = make_float4(0.f, 0.f, 0.f, 0.f);                                                \
+        if (FAST) {                                                                                 \
+          if (row_ < rows_) v_ = ldg4(a.x + (base_ + row_) * a.ldx + col_);                         \
+        } else if (row_ < rows_ && col_ < K) {                                                      \
+          const float* p_ = a.x + (base_ + row_) * a.ldx + col_;                                    \
+          if (a.xvec) {                                                                             \
+            v_ = ldg4(p_);                                                                          \
+          } else {                                                                                  \
+            v_.x = __ldg(p_);                                                                       \
+            if (col_ + 1 < K) v_.y = __ldg(p_ + 1);                                                 \
+            if (col_ + 2 < K) v_.z = __ldg(p_ + 2);                                                 \
+            if (col_ + 3 < K) v_.w = __ldg(p_ + 3);                                                 \
+          }                                                                                         \
+        }                                                                                           \
+        pre[SLOT][q] = v_;                                                                          \
+      }                                                                                             \
+    }
+    // prologue (BatchNorm affine / ReLU) + zeroing of dead rows and the K tail + head/tail split of one K-block
+    auto store_block = [&](int stage, const Cur& c, const float4 (&pv)[4]) {
+      const int g = (int)(c.tile / tpg);
+      const long long row0 = (c.tile - (long long)g * tpg) * TC_BM;
+      const int rows = (int)((a.R - row0 < TC_BM) ? (a.R - row0) : TC_BM);
       uint8_t* sh = ring + stage * 2 * TC_BLK_BYTES;
       uint8_t* sl = sh + TC_BLK_BYTES;
+      const int col = c.kb * TC_KB + c4 * 4;
+      float4 pa4 = make_float4(1.f, 1.f, 1.f, 1.f), pc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.pro) {   // coefficients of columns >= K are (1, 0)
+        pa4 = *reinterpret_cast<const float4*>(&s_pa[g * 128 + col]);
+        pc4 = *reinterpret_cast<const float4*>(&s_pc[g * 128 + col]);
+      }
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int f = tid + TC_WORKERS * q;
-        const int row = f >> 3, c4 = f & 7;
-        const int col = kb * TC_KB + c4 * 4;
-        const float4 pv = (kb == 0) ? pre[q] : (kb == 1) ? pre[2 + q] : (kb == 2) ? pre[4 + q] : pre[6 + q];
-        float t[4] = {pv.x, pv.y, pv.z, pv.w};
+      for (int q = 0; q < 4; ++q) {
+        const int row = prow + 32 * q;
+        float t[4] = {pv[q].x, pv[q].y, pv[q].z, pv[q].w};
         const bool live = row < rows;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (live && col + j < K) {
-            if (a.pro) {
-              const float u = fmaf(s_pa[g * 128 + col + j], t[j], s_pc[g * 128 + col + j]);
-              t[j] = (a.pro == 2) ? fmaxf(u, 0.f) : u;
-            }
-          } else {
-            t[j] = 0.f;
+        if (a.pro) {
+          t[0] = fmaf(pa4.x, t[0], pc4.x); t[1] = fmaf(pa4.y, t[1], pc4.y);
+          t[2] = fmaf(pa4.z, t[2], pc4.z); t[3] = fmaf(pa4.w, t[3], pc4.w);
+          if (a.pro == 2) {
+            t[0] = fmaxf(t[0], 0.f); t[1] = fmaxf(t[1], 0.f); t[2] = fmaxf(t[2], 0.f); t[3] = fmaxf(t[3], 0.f);
           }
+        }
+        if (FAST) {
+          if (!live) t[0] = t[1] = t[2] = t[3] = 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (!(live && col + j < K)) t[j] = 0.f;
         }
         float4 h, l;
         tc_split(t[0], h.x, l.x);
@@ -230,117 +272,155 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
         *reinterpret_cast<float4*>(sl + off) = l;
       }
     };
+    auto l2_ahead = [&](long long tile) {   // one bulk prefetch per tile: its rows are contiguous
+      const long long pt = tile + (long long)TC_L2_AHEAD * gridDim.x;
+      if (pt < ntiles) {
+        const int pg = (int)(pt / tpg);
+        const long long prow0 = (pt - (long long)pg * tpg) * TC_BM;
+        const int prows = (int)((a.R - prow0 < TC_BM) ? (a.R - prow0) : TC_BM);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.x + ((long long)pg * a.R + prow0) * a.ldx),
+                     "r"((uint32_t)(prows * a.ldx * 4)) : "memory");
+      }
+    };
+    auto publish = [&](int stage) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[stage]);
+    };
 
-    long long tile = blockIdx.x;
-    unsigned cnt = 0, tile_it = 0;
-    if (tile < ntiles) load_tile(tile);
-
-    while (tile < ntiles) {
+    Cur cur{(long long)blockIdx.x, 0}, nxt = cur;
+    TC_LOAD_BLOCK(nxt, 0)
+    advance(nxt);
+    TC_LOAD_BLOCK(nxt, 1)
+    advance(nxt);
+    unsigned cnt = 0;
+    while (cur.tile < ntiles) {
+      // position cnt (even) -> stage 0 / slot 0
+      if (cnt >= 2) mbar_wait(&mma_done[0], ((cnt >> 1) - 1) & 1);   // MMAs that read this stage have retired
+      if (tid == 0 && cur.kb == 0 && (FAST || a.xvec)) l2_ahead(cur.tile);
+      store_block(0, cur, pre[0]);
+      publish(0);
+      TC_LOAD_BLOCK(nxt, 0)
+      advance(nxt);
+      advance(cur);
+      ++cnt;
+      if (cur.tile >= ntiles) break;
+      // position cnt (odd) -> stage 1 / slot 1
+      if (cnt >= 2) mbar_wait(&mma_done[1], ((cnt >> 1) - 1) & 1);
+      if (tid == 0 && cur.kb == 0 && (FAST || a.xvec)) l2_ahead(cur.tile);
+      store_block(1, cur, pre[1]);
+      publish(1);
+      TC_LOAD_BLOCK(nxt, 1)
+      advance(nxt);
+      advance(cur);
+      ++cnt;
+    }
+#undef TC_LOAD_BLOCK
+  } else {
+    // ================================================================================================= epilogue
+    // warp e owns TMEM lanes [32 q, 32 q + 32) and the column blocks cb = (e >> 2) and (e >> 2) + 2
+    const int e = warp - TC_PROD / 32, eq = e & 3;
+    float* wst = estage + e * (32 * 32);               // [32 rows][32 cols], 16-byte chunks XOR-swizzled by (row & 7)
+    double st_s[2][TC_MAXG] = {{0.0, 0.0}, {0.0, 0.0}}, st_q[2][TC_MAXG] = {{0.0, 0.0}, {0.0, 0.0}};
+    unsigned ti = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
       const int g = (int)(tile / tpg);
       const long long row0 = (tile - (long long)g * tpg) * TC_BM;
       const int rows = (int)((a.R - row0 < TC_BM) ? (a.R - row0) : TC_BM);
       const long long base = (long long)g * a.R + row0;
-      const long long ntile = tile + gridDim.x;
-
-      for (int kb = 0; kb < nkb; ++kb, ++cnt) {
-        const int stage = cnt & 1;
-        const unsigned use = cnt >> 1;
-        if (use > 0) mbar_wait(&mma_done[stage], (use - 1) & 1);   // MMAs that read this stage have retired
-        store_block(stage, kb, g, rows);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        worker_sync();
-        if (tid == 0) mbar_arrive(&full[stage]);
-      }
-      // registers of this tile are consumed: request the whole next tile while the tensor core + epilogue run
-      if (ntile < ntiles) load_tile(ntile);
-
-      // ---------------------------------------------------------------------------------------------- epilogue
-      mbar_wait(&acc_done, tile_it & 1);
+      const uint32_t buf = ti & 1u;
+      mbar_wait(&acc_done[buf], (ti >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float* stg = reinterpret_cast<float*>(ring);   // [128][128] fp32, float4 chunk index XOR (row & 31)
-      {
-        const int q = warp & 3, cb = warp >> 2;       // TMEM lane quarter, 32-column block
-        const int row = q * 32 + lane;
-        const int c0 = cb * 32;
-        if (c0 < a.NP) {
-          uint32_t v[32];
-          TC_LD32(v, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0);
+      const int row = eq * 32 + lane;
+      const bool live = row < rows;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int ec0 = ((e >> 2) + 2 * hh) * 32;
+        uint32_t v[32];
+        if (ec0 < a.NP) {
+          TC_LD32(v, tmem + buf * 128u + ((uint32_t)(eq * 32) << 16) + (uint32_t)ec0);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        if (hh == 1) {   // both blocks are in registers / done: hand the accumulator back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_free[buf]);
+        }
+        if (ec0 >= a.NP) continue;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float o[4];
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[ec0 + i * 4]);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          float o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int col = c0 + i * 4 + j;
-              float t = __uint_as_float(v[i * 4 + j]) + s_bias[col];
-              if (a.accumulate && row < rows && col < N) t += a.y[(base + row) * a.ldy + col];
-              if (a.relu) t = fmaxf(t, 0.f);
-              o[j] = (col < N) ? t : 0.f;
+          for (int j = 0; j < 4; ++j) {
+            const int col = ec0 + i * 4 + j;
+            float t = __uint_as_float(v[i * 4 + j]) + bb[j];
+            if (!FAST && a.accumulate && live && col < N) t += a.y[(base + row) * a.ldy + col];
+            if (a.relu) t = fmaxf(t, 0.f);
+            o[j] = ((FAST || col < N) && live) ? t : 0.f;
+          }
+          *reinterpret_cast<float4*>(wst + lane * 32 + ((i ^ (lane & 7)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        __syncwarp();
+        // coalesced write-back: 4 rows x 128 contiguous bytes per instruction
+        {
+          const int c = lane & 7;
+          if (FAST || ec0 + c * 4 < a.ycols) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + (lane >> 3);
+              const int grow = eq * 32 + r;
+              if (grow < rows) {
+                const float4 o4 = *reinterpret_cast<const float4*>(wst + r * 32 + ((c ^ (r & 7)) << 2));
+                float* yp = a.y + (base + grow) * a.ldy + ec0 + c * 4;
+                if (FAST || (a.yvec && ec0 + c * 4 + 3 < a.ycols)) {
+                  *reinterpret_cast<float4*>(yp) = o4;
+                } else {
+                  const float t4[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (ec0 + c * 4 + j < a.ycols) yp[j] = t4[j];
+                }
+              }
             }
-            const int ch = (c0 >> 2) + i;
-            *reinterpret_cast<float4*>(stg + row * 128 + ((ch ^ (row & 31)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      worker_sync();
-      // coalesced write-back: one warp per row (8 rows per warp), lanes over float4 chunks
-      {
-        const int col0 = lane * 4;
-        if (col0 < a.ycols) {
-#pragma unroll 4
-          for (int row = warp; row < rows; row += TC_WORKERS / 32) {
-            const float4 o = *reinterpret_cast<const float4*>(stg + row * 128 + ((lane ^ (row & 31)) << 2));
-            float* yrow = a.y + (base + row) * a.ldy;
-            if (a.yvec) {
-              *reinterpret_cast<float4*>(yrow + col0) = o;
-            } else {
-              const float t[4] = {o.x, o.y, o.z, o.w};
+        if (a.stats) {   // lane -> column ec0 + lane over the block's 32 rows (conflict-free LDS.32)
+          float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (col0 + j < a.ycols) yrow[col0 + j] = t[j];
-            }
+          for (int r = 0; r < 32; ++r) {
+            const float t = wst[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
+            s1 += t;
+            s2 = fmaf(t, t, s2);
           }
+          if (g == 0) { st_s[hh][0] += (double)s1; st_q[hh][0] += (double)s2; }
+          else        { st_s[hh][1] += (double)s1; st_q[hh][1] += (double)s2; }
         }
+        __syncwarp();
       }
-      if (a.stats) {
-        // column sums in fp64: thread -> (column, row quarter); two independent chains per thread
-        const int col = tid & 127, part = tid >> 7;
+    }
+    if (a.stats) {   // 4 warps (lane quarters) per column, once per kernel
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int col = ((e >> 2) + 2 * hh) * 32 + lane;
         if (col < N) {
-          double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
-          const int r_beg = part * 32;
-          const int r_end = (rows < r_beg + 32) ? rows : r_beg + 32;
-          int row = r_beg;
-          for (; row + 1 < r_end; row += 2) {
-            const float t0 = stg[row * 128 + ((((col >> 2) ^ (row & 31)) << 2) | (col & 3))];
-            const float t1 = stg[(row + 1) * 128 + ((((col >> 2) ^ ((row + 1) & 31)) << 2) | (col & 3))];
-            s0 += (double)t0; q0 += (double)t0 * (double)t0;
-            s1 += (double)t1; q1 += (double)t1 * (double)t1;
+#pragma unroll
+          for (int g = 0; g < TC_MAXG; ++g) {
+            if (g < a.G) {
+              atomicAdd(a.stats + (long long)(g * 2 + 0) * N + col, st_s[hh][g]);
+              atomicAdd(a.stats + (long long)(g * 2 + 1) * N + col, st_q[hh][g]);
+            }
           }
-          if (row < r_end) {
-            const float t0 = stg[row * 128 + ((((col >> 2) ^ (row & 31)) << 2) | (col & 3))];
-            s0 += (double)t0; q0 += (double)t0 * (double)t0;
-          }
-          atomicAdd(&sacc[(g * 2 + 0) * 128 + col], s0 + s1);
-          atomicAdd(&sacc[(g * 2 + 1) * 128 + col], q0 + q1);
         }
       }
-      worker_sync();   // staging (= ring) is free again; the TMEM accumulator has been drained
-      tile = ntile;
-      ++tile_it;
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (a.stats) {
-    for (int idx = tid; idx < a.G * 2 * 128; idx += TC_THREADS) {
-      const int col = idx & 127, gj = idx >> 7;
-      if (col < N && sacc[idx] != 0.0) atomicAdd(a.stats + (long long)gj * N + col, sacc[idx]);
-    }
-  }
-  if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+  if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
 // Returns SB_ERR_UNSUPPORTED (without setting an error) when the shape is better served by the FFMA kernel.
@@ -356,17 +436,20 @@ int sb_linear_tc_launch(const float* x, int64_t ldx, const float* w, int64_t w_r
   a.xvec = (ldx % 4 == 0) && ((uintptr_t)x % 16 == 0);
   a.yvec = (ldy % 4 == 0) && ((uintptr_t)y % 16 == 0);
   a.ycols = (ycols < a.NP) ? ycols : a.NP;
-  const size_t smem = (size_t)2 * a.nkb * TC_BLK_BYTES + 4 * TC_BLK_BYTES + 1024;
+  const size_t smem = (size_t)2 * a.nkb * TC_BLK_BYTES + 4 * TC_BLK_BYTES + TC_ESTAGE_BYTES;
   static bool configured = false;
   if (!configured) {
-    SB_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 2 * 4 * TC_BLK_BYTES + 4 * TC_BLK_BYTES + 1024));
+    const int mx = 2 * 4 * TC_BLK_BYTES + 4 * TC_BLK_BYTES + TC_ESTAGE_BYTES;
+    SB_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    SB_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     configured = true;
   }
   const long long ntiles = sb_ceil_div(R, TC_BM) * G;
   long long grid = sb_num_sms();
   if (grid > ntiles) grid = ntiles;
-  linear_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, st>>>(a);
+  const bool fast = a.xvec && a.yvec && (K % 32 == 0) && (N % 32 == 0) && !accumulate && a.ycols == N;
+  if (fast) linear_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, st>>>(a);
+  else linear_tc_kernel<false><<<(unsigned)grid, TC_THREADS, smem, st>>>(a);
   SB_CHECK_LAUNCH("sb_linear_fwd(tcgen05)");
   return SB_OK;
 }

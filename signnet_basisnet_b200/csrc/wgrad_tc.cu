@@ -4,7 +4,8 @@
 // tf32 the only MN-major shared-memory layout is SWIZZLE_128B_BASE32B (4-row x 128-byte atoms, 32-byte XOR swizzle).
 //
 // Persistent CTA per SM, 16 worker warps + 1 MMA warp.  Workers stream 32-row chunks of g and x (register prefetch two
-// chunks ahead), apply the forward prologue to x (BatchNorm affine / ReLU recomputed, never stored), split head/tail
+// chunks ahead, backed by bulk L2 prefetches WT_L2_AHEAD chunks ahead: with registers alone only 64 KB per SM were in
+// flight and the kernel sat at 22 % of DRAM bandwidth stalled on the loads, profiles/r1g_wgrad_tc_ncu.csv), apply the forward prologue to x (BatchNorm affine / ReLU recomputed, never stored), split head/tail
 // and write the four operand blocks of a 3-stage ring; the MMA warp issues 12 x UMMA 128 x K x 8 per chunk into one
 // [128 x 128] fp32 accumulator in tensor memory that lives for the whole kernel; per-CTA partials are then added in a
 // fixed order by wgrad_reduce_kernel (deterministic, no float atomics).
@@ -18,6 +19,7 @@
 #define WT_WORKERS 512
 #define WT_THREADS (WT_WORKERS + 32)
 #define WT_MAXG 2
+#define WT_L2_AHEAD 6   // chunks requested into L2 ahead of the register prefetch (cp.async.bulk.prefetch.L2)
 
 struct WgTcArgs {
   const float* g;
@@ -59,6 +61,12 @@ __device__ __forceinline__ void wt_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void wt_worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(WT_WORKERS) : "memory"); }
 
+__device__ __forceinline__ void wt_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// FAST: N == K == 128 and 16-byte aligned rows -> no per-element bounds / alignment predicates are compiled in.
+template <bool FAST>
 __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem;   // [WT_STAGES][g_hi | g_lo | x_hi | x_lo]
@@ -134,7 +142,12 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
         const int idx = tid + WT_WORKERS * q;
         const int row = (idx >> 3) & 31, col = (idx >> 8) * 32 + (idx & 7) * 4;
         float4 vg = make_float4(0.f, 0.f, 0.f, 0.f), vx = vg;
-        if (row < rows) {
+        if (FAST) {
+          if (row < rows) {
+            vg = ldg4(a.g + (base + row) * a.ldg + col);
+            vx = ldg4(a.x + (base + row) * a.ldx + col);
+          }
+        } else if (row < rows) {
           if (col < N) {
             const float* p = a.g + (base + row) * a.ldg + col;
             if (a.gvec) {
@@ -175,19 +188,26 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
         const float4 vg = slot ? pg1[q] : pg0[q], vx = slot ? px1[q] : px0[q];
         float tg[4] = {vg.x, vg.y, vg.z, vg.w};
         float tx[4] = {vx.x, vx.y, vx.z, vx.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (!(live && col + j < N)) tg[j] = 0.f;
-          if (live && col + j < K) {
-            if (a.pro) {
-              const float u = fmaf(s_pa[g * 128 + col + j], tx[j], s_pc[g * 128 + col + j]);
-              tx[j] = (a.pro == 2) ? fmaxf(u, 0.f) : u;
-            }
-          } else {
-            tx[j] = 0.f;
+        if (a.pro) {   // coefficients of columns >= K are (1, 0): harmless, those entries are zeroed below
+          const float4 pa4 = *reinterpret_cast<const float4*>(&s_pa[g * 128 + col]);
+          const float4 pc4 = *reinterpret_cast<const float4*>(&s_pc[g * 128 + col]);
+          tx[0] = fmaf(pa4.x, tx[0], pc4.x); tx[1] = fmaf(pa4.y, tx[1], pc4.y);
+          tx[2] = fmaf(pa4.z, tx[2], pc4.z); tx[3] = fmaf(pa4.w, tx[3], pc4.w);
+          if (a.pro == 2) {
+            tx[0] = fmaxf(tx[0], 0.f); tx[1] = fmaxf(tx[1], 0.f); tx[2] = fmaxf(tx[2], 0.f); tx[3] = fmaxf(tx[3], 0.f);
           }
-          dbs[q][j] += tg[j];
         }
+        if (FAST) {
+          if (!live) { tg[0] = tg[1] = tg[2] = tg[3] = 0.f; tx[0] = tx[1] = tx[2] = tx[3] = 0.f; }
+        } else if (!(live && col + 3 < N && col + 3 < K)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!(live && col + j < N)) tg[j] = 0.f;
+            if (!(live && col + j < K)) tx[j] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dbs[q][j] += tg[j];
         float4 h, l;
         const uint32_t off = (uint32_t)(blk * 4096 + row * 128 + (((c4 >> 1) ^ (row & 3)) << 5) + (c4 & 1) * 16);
         wt_split(tg[0], h.x, l.x); wt_split(tg[1], h.y, l.y); wt_split(tg[2], h.z, l.z); wt_split(tg[3], h.w, l.w);
@@ -199,8 +219,21 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
       }
     };
 
+    // one thread asks L2 for a whole chunk (rows are contiguous: 32 x ld floats per operand)
+    const bool l2ok = FAST || (a.gvec && a.xvec);
+    auto l2_chunk = [&](long long cc) {
+      const int g = (int)(cc / cpg);
+      const long long row0 = (cc - (long long)g * cpg) * WT_ROWS;
+      const int rows = (int)((a.R - row0 < WT_ROWS) ? (a.R - row0) : WT_ROWS);
+      const long long base = (long long)g * a.R + row0;
+      wt_prefetch_l2(a.g + base * a.ldg, (uint32_t)(rows * a.ldg * 4));
+      wt_prefetch_l2(a.x + base * a.ldx, (uint32_t)(rows * a.ldx * 4));
+    };
     long long c = blockIdx.x;
     unsigned cnt = 0;
+    if (tid == 32 && l2ok)
+      for (int s = 2; s < WT_L2_AHEAD; ++s)
+        if (c + (long long)s * gridDim.x < nch) l2_chunk(c + (long long)s * gridDim.x);
     if (c < nch) load_chunk(c, 0);
     if (c + gridDim.x < nch) load_chunk(c + gridDim.x, 1);
     for (; c < nch; c += gridDim.x, ++cnt) {
@@ -213,6 +246,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       wt_worker_sync();
       if (tid == 0) mbar_arrive(&full[stage]);
+      if (tid == 32 && l2ok) {
+        const long long cl = c + (long long)WT_L2_AHEAD * gridDim.x;
+        if (cl < nch) l2_chunk(cl);
+      }
       const long long c2 = c + 2ll * gridDim.x;   // the slot just consumed is refilled two chunks ahead
       if (c2 < nch) load_chunk(c2, slot);
     }
@@ -289,10 +326,12 @@ int sb_wgrad_tc_launch(const float* gy, int64_t ldg, const float* x, int64_t ldx
   const size_t smem = (size_t)WT_STAGES * WT_STAGE_BYTES + 1024;
   static bool configured = false;
   if (!configured) {
-    SB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  wgrad_tc_kernel<<<(unsigned)grid, WT_THREADS, smem, st>>>(a);
+  if (a.gvec && a.xvec && N == 128 && K == 128) wgrad_tc_kernel<true><<<(unsigned)grid, WT_THREADS, smem, st>>>(a);
+  else wgrad_tc_kernel<false><<<(unsigned)grid, WT_THREADS, smem, st>>>(a);
   SB_CHECK_LAUNCH("sb_linear_wgrad(tcgen05)");
   return sb_wgrad_reduce_launch(a.part_w, a.part_b, (int)grid, 128, 128, N, K, dw, dw_rs, dw_cs, db, accumulate, st);
 }

@@ -28,6 +28,7 @@
 #define TC_PROD 256                    // producer threads (warps 0..7); warps 8..15 are the epilogue
 #define TC_THREADS (TC_WORKERS + 32)
 #define TC_MAXG 2
+static_assert(TC_MAXG == 2, "the tile -> group mapping below assumes at most two groups");
 #define TC_ESTAGE_BYTES (8 * 32 * 32 * 4)    // per-epilogue-warp [32 rows][32 cols] fp32 transposition tile
 #define TC_L2_AHEAD 3   // tiles requested into L2 ahead of the one-tile register prefetch
 
@@ -65,9 +66,9 @@ __device__ __forceinline__ uint32_t tc_sw128(int r, int c) {
 // head = x rounded to nearest tf32 (10-bit mantissa), tail = x - head (exact in fp32; the tensor core keeps its top
 // 11 bits).  Round-to-nearest instead of truncation removes the systematic sign-correlated bias of the heads.
 __device__ __forceinline__ void tc_split(float x, float& h, float& l) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  h = __uint_as_float(u);
+  // == cvt.rna.tf32.f32 for finite x (adding half an ulp of the 10-bit mantissa to the magnitude bits, then truncating),
+  // in two ALU instructions instead of the five the conversion expands to
+  h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
   l = x - h;
 }
 __device__ __forceinline__ void tc_mma(uint32_t tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
@@ -199,6 +200,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
     // ================================================================================================ producers
     // thread -> float4 column c4 of rows (tid >> 3) + 32 q, q < 4, of every K-block
     const int prow = tid >> 3, c4 = tid & 7;
+    const float* xthread = a.x + (long long)prow * a.ldx + c4 * 4;   // this thread's element of row 0, K-block 0
+    const long long xstride32 = 32 * a.ldx;
     float4 pre[2][4];                                  // two K-blocks in flight (slot = position parity)
     struct Cur { long long tile; int kb; };
     auto advance = [&](Cur& c) {
@@ -206,18 +209,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
     };
 #define TC_LOAD_BLOCK(CUR, SLOT)                                                                    \
     if ((CUR).tile < ntiles) {                                                                      \
-      const int g_ = (int)((CUR).tile / tpg);                                                       \
+      const int g_ = ((CUR).tile >= tpg) ? 1 : 0;                                                      \
       const long long row0_ = ((CUR).tile - (long long)g_ * tpg) * TC_BM;                           \
       const int rows_ = (int)((a.R - row0_ < TC_BM) ? (a.R - row0_) : TC_BM);                       \
       const long long base_ = (long long)g_ * a.R + row0_;                                          \
       const int col_ = (CUR).kb * TC_KB + c4 * 4;                                                   \
+      const float* pb_ = xthread + base_ * a.ldx + (CUR).kb * TC_KB;                                \
       _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                               \
         const int row_ = prow + 32 * q;                                                             \
         float4 v_ = make_float4(0.f, 0.f, 0.f, 0.f);                                                \
         if (FAST) {                                                                                 \
-          if (row_ < rows_) v_ = ldg4(a.x + (base_ + row_) * a.ldx + col_);                         \
+          if (row_ < rows_) v_ = ldg4(pb_ + q * xstride32);                                         \
         } else if (row_ < rows_ && col_ < K) {                                                      \
-          const float* p_ = a.x + (base_ + row_) * a.ldx + col_;                                    \
+          const float* p_ = pb_ + q * xstride32;                                                    \
           if (a.xvec) {                                                                             \
             v_ = ldg4(p_);                                                                          \
           } else {                                                                                  \
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
     }
     // prologue (BatchNorm affine / ReLU) + zeroing of dead rows and the K tail + head/tail split of one K-block
     auto store_block = [&](int stage, const Cur& c, const float4 (&pv)[4]) {
-      const int g = (int)(c.tile / tpg);
+      const int g = (c.tile >= tpg) ? 1 : 0;   // G <= TC_MAXG = 2: no 64-bit division in the hot loop
       const long long row0 = (c.tile - (long long)g * tpg) * TC_BM;
       const int rows = (int)((a.R - row0 < TC_BM) ? (a.R - row0) : TC_BM);
       uint8_t* sh = ring + stage * 2 * TC_BLK_BYTES;
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
     auto l2_ahead = [&](long long tile) {   // one bulk prefetch per tile: its rows are contiguous
       const long long pt = tile + (long long)TC_L2_AHEAD * gridDim.x;
       if (pt < ntiles) {
-        const int pg = (int)(pt / tpg);
+        const int pg = (pt >= tpg) ? 1 : 0;
         const long long prow0 = (pt - (long long)pg * tpg) * TC_BM;
         const int prows = (int)((a.R - prow0 < TC_BM) ? (a.R - prow0) : TC_BM);
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.x + ((long long)pg * a.R + prow0) * a.ldx),
@@ -322,10 +326,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
     // warp e owns TMEM lanes [32 q, 32 q + 32) and the column blocks cb = (e >> 2) and (e >> 2) + 2
     const int e = warp - TC_PROD / 32, eq = e & 3;
     float* wst = estage + e * (32 * 32);               // [32 rows][32 cols], 16-byte chunks XOR-swizzled by (row & 7)
+    const long long ystride4 = 4 * a.ldy;
     double st_s[2][TC_MAXG] = {{0.0, 0.0}, {0.0, 0.0}}, st_q[2][TC_MAXG] = {{0.0, 0.0}, {0.0, 0.0}};
     unsigned ti = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
-      const int g = (int)(tile / tpg);
+      const int g = (tile >= tpg) ? 1 : 0;
       const long long row0 = (tile - (long long)g * tpg) * TC_BM;
       const int rows = (int)((a.R - row0 < TC_BM) ? (a.R - row0) : TC_BM);
       const long long base = (long long)g * a.R + row0;
@@ -367,6 +372,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
         // coalesced write-back: 4 rows x 128 contiguous bytes per instruction
         {
           const int c = lane & 7;
+          float* ybase = a.y + (base + eq * 32 + (lane >> 3)) * a.ldy + ec0 + c * 4;
           if (FAST || ec0 + c * 4 < a.ycols) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -374,7 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
               const int grow = eq * 32 + r;
               if (grow < rows) {
                 const float4 o4 = *reinterpret_cast<const float4*>(wst + r * 32 + ((c ^ (r & 7)) << 2));
-                float* yp = a.y + (base + grow) * a.ldy + ec0 + c * 4;
+                float* yp = ybase + it * ystride4;
                 if (FAST || (a.yvec && ec0 + c * 4 + 3 < a.ycols)) {
                   *reinterpret_cast<float4*>(yp) = o4;
                 } else {

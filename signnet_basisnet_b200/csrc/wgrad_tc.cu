@@ -46,9 +46,8 @@ __device__ __forceinline__ uint64_t wt_make_desc(uint32_t saddr) {
   return d;
 }
 __device__ __forceinline__ void wt_split(float x, float& h, float& l) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  h = __uint_as_float(u);
+  // == cvt.rna.tf32.f32 for finite x, in two ALU instructions (see tc_split in linear_tc.cu)
+  h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
   l = x - h;
 }
 __device__ __forceinline__ void wt_mma(uint32_t tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
@@ -85,7 +84,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
   }
   if (tid == 0) {
     for (int s = 0; s < WT_STAGES; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], WT_WORKERS / 32);
       mbar_init(&mma_done[s], 1);
     }
     mbar_init(&acc_done, 1);
@@ -133,7 +132,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
     float4 pg0[2], pg1[2], px0[2], px1[2];   // two prefetch slots (selected with predicated moves, no local memory)
     float dbs[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     auto load_chunk = [&](long long c, int slot) {
-      const int g = (int)(c / cpg);
+      const int g = (c >= cpg) ? 1 : 0;   // G <= WT_MAXG = 2: no 64-bit division in the hot loop
       const long long row0 = (c - (long long)g * cpg) * WT_ROWS;
       const int rows = (int)((a.R - row0 < WT_ROWS) ? (a.R - row0) : WT_ROWS);
       const long long base = (long long)g * a.R + row0;
@@ -175,7 +174,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
       }
     };
     auto store_chunk = [&](int stage, int slot, long long c) {
-      const int g = (int)(c / cpg);
+      const int g = (c >= cpg) ? 1 : 0;   // G <= WT_MAXG = 2: no 64-bit division in the hot loop
       const long long row0 = (c - (long long)g * cpg) * WT_ROWS;
       const int rows = (int)((a.R - row0 < WT_ROWS) ? (a.R - row0) : WT_ROWS);
       uint8_t* sb = ring + stage * WT_STAGE_BYTES;
@@ -222,7 +221,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
     // one thread asks L2 for a whole chunk (rows are contiguous: 32 x ld floats per operand)
     const bool l2ok = FAST || (a.gvec && a.xvec);
     auto l2_chunk = [&](long long cc) {
-      const int g = (int)(cc / cpg);
+      const int g = (cc >= cpg) ? 1 : 0;
       const long long row0 = (cc - (long long)g * cpg) * WT_ROWS;
       const int rows = (int)((a.R - row0 < WT_ROWS) ? (a.R - row0) : WT_ROWS);
       const long long base = (long long)g * a.R + row0;
@@ -244,8 +243,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
       store_chunk(stage, slot, c);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      wt_worker_sync();
-      if (tid == 0) mbar_arrive(&full[stage]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[stage]);   // one arrival per worker warp: no block-wide barrier per chunk
       if (tid == 32 && l2ok) {
         const long long cl = c + (long long)WT_L2_AHEAD * gridDim.x;
         if (cl < nch) l2_chunk(cl);

@@ -275,6 +275,16 @@ static bool use_tc() {
   return g_use_tc == 1;
 }
 
+int sb_rank1_fwd_launch(const float* x, int64_t ldx, const float* w, int64_t w_rs, const float* bias, float* y,
+                        int64_t ldy, int64_t R, int32_t G, int32_t N, int32_t ycols, int32_t pro, const float* pa,
+                        const float* pc, int32_t relu, double* stats, cudaStream_t st);
+int sb_rowdot_fwd_launch(const float* x, int64_t ldx, const float* w, int64_t w_cs, const float* bias, float* y,
+                         int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t pro, const float* pa, const float* pc,
+                         int32_t relu, cudaStream_t st);
+int sb_rank1_wgrad_launch(const float* gy, int64_t ldg, const float* x, int64_t ldx, int64_t R, int32_t G, int32_t N,
+                          int32_t pro, const float* pa, const float* pc, float* dw, int64_t dw_rs, float* db,
+                          int32_t accumulate, float* workspace, cudaStream_t st);
+
 template <int BN>
 static int launch_linear(const LinArgs& a, cudaStream_t st) {
   static size_t configured = 0;
@@ -303,6 +313,16 @@ extern "C" int sb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_
   SB_CHECK_ARG(pro >= 0 && pro <= 2 && (pro == 0 || (pa && pc)), "sb_linear_fwd: bad prologue");
   if (R == 0) return SB_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  // degenerate shapes of the first phi layer: outer product (K = 1) / row dot product (N = 1) streaming kernels
+  if (K == 1 && N <= 128 && !accumulate) {
+    const int rc = sb_rank1_fwd_launch(x, ldx, w, w_rs, bias, y, ldy, R, G, N, (int)(ldy < 128 ? ldy : 128), pro, pa, pc,
+                                       relu, stats, st);
+    if (rc != SB_ERR_UNSUPPORTED) return rc;
+  }
+  if (N == 1 && !accumulate && !stats && (!pro || K <= 128)) {
+    const int rc = sb_rowdot_fwd_launch(x, ldx, w, w_cs, bias, y, ldy, R, G, K, pro, pa, pc, relu, st);
+    if (rc != SB_ERR_UNSUPPORTED) return rc;
+  }
   // Host-side blocking over N (<= 128 per launch) and K (<= 128 per launch, accumulating).
   for (int n0 = 0; n0 < N; n0 += 128) {
     const int nn = (N - n0 < 128) ? (N - n0) : 128;
@@ -595,6 +615,10 @@ extern "C" int sb_linear_wgrad(const float* gy, int64_t ldg, const float* x, int
       if (db) SB_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * N, st));
     }
     return SB_OK;
+  }
+  if (K == 1 && N <= 128) {   // first phi layer: dW0[n] = sum_rows g[row, n] * f(x[row])
+    const int rc = sb_rank1_wgrad_launch(gy, ldg, x, ldx, R, G, N, pro, pa, pc, dw, dw_rs, db, accumulate, workspace, st);
+    if (rc != SB_ERR_UNSUPPORTED) return rc;
   }
   for (int n0 = 0; n0 < N; n0 += 128) {
     const int nn = (N - n0 < 128) ? (N - n0) : 128;

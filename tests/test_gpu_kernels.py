@@ -160,12 +160,12 @@ def test_gin_aggregate_backward_mode(C, k, masked):
                                                (1, 64, 0, False, False), (1, 1, 0, False, False),
                                                (67, 4, 2, False, True), (200, 70, 0, True, True),
                                                (6, 130, 0, False, True)])
-def test_linear_fwd_and_stats(K, N, pro, relu, bias):
+def test_linear_fwd_and_stats(K, N, pro, relu, bias, R=333):
     from signnet_basisnet_b200.functional import linear_fwd
     from signnet_basisnet_b200.layout import pad4
 
     torch.manual_seed(K * 131 + N)
-    G, R = 2, 333
+    G = 2
     ldx, ldy = (pad4(K) if K > 1 else 1), pad4(N)
     x = torch.zeros(G, R, ldx)
     x[..., :K] = torch.randn(G, R, K)
@@ -196,12 +196,12 @@ def test_linear_fwd_and_stats(K, N, pro, relu, bias):
 
 @pytest.mark.parametrize("K,N,pro", [(128, 128, 0), (128, 128, 2), (64, 64, 2), (95, 95, 1), (1, 64, 0), (64, 1, 0),
                                      (70, 200, 0), (130, 12, 0)])
-def test_linear_wgrad(K, N, pro):
+def test_linear_wgrad(K, N, pro, R=777):
     from signnet_basisnet_b200.functional import linear_wgrad
     from signnet_basisnet_b200.layout import pad4
 
     torch.manual_seed(K * 7 + N)
-    G, R = 2, 777
+    G = 2
     ldx, ldg = (pad4(K) if K > 1 else 1), (pad4(N) if N > 1 else 1)
     x = torch.zeros(G, R, ldx)
     x[..., :K] = torch.randn(G, R, K)
@@ -221,3 +221,17 @@ def test_linear_wgrad(K, N, pro):
                  pc=pc.to(DEV) if pro else None)
     assert_close_rel(dW.cpu(), ref_w.float(), 1e-5, what="dW")
     assert_close_rel(db.cpu(), ref_b.float(), 1e-5, what="db")
+
+
+@pytest.mark.parametrize("K,N,pro,relu,bias", [(1, 128, 0, False, False), (1, 64, 1, True, True), (1, 95, 2, False, True),
+                                               (128, 1, 0, False, False), (95, 1, 2, True, True),
+                                               (128, 128, 2, False, True), (64, 128, 0, True, False)])
+def test_linear_fwd_streaming_sizes(K, N, pro, relu, bias):
+    """Row counts above the small-problem threshold: the rank-1 / row-dot kernels of the first phi layer
+    (csrc/linear_rank1.cu) and the tcgen05 path (csrc/linear_tc.cu), including a ragged last tile."""
+    test_linear_fwd_and_stats(K, N, pro, relu, bias, R=2999)
+
+
+@pytest.mark.parametrize("K,N,pro", [(1, 128, 0), (1, 64, 2), (1, 95, 1), (128, 128, 2)])
+def test_linear_wgrad_streaming_sizes(K, N, pro):
+    test_linear_wgrad(K, N, pro, R=2999)

@@ -195,6 +195,16 @@ int sb_layernorm_fwd(const float* a, const float* b, const float* w, const float
 int sb_layernorm_bwd(const float* g, const float* x, const float* stat, const float* w, int64_t ld, int64_t R,
                      int32_t C, float* dx, double* dwb, void* stream);
 
+/* ---- K9: BasisNet IGN phi (LearningFilters/ign.py:344-374 contractions_2_to_1, normalization 'inf') ------------------
+ * ops[(e*n + i)*ldo + 0..4] = { P_ii, tr(P)/n, sum_j P_ij/n, sum_j P_ji/n, sum_ij P_ij/n^2 } of the eigenspace projectors
+ * P_e = V_e V_e^T, columns 5..ldo-1 zero.  _factors reads only the eigenvector blocks V[:, col0[e] .. col0[e]+mult)
+ * (4 n mult bytes per eigenspace; the projector the reference materialises in training.py:59-61 never exists);
+ * _projectors takes the reference's materialised input P [b, n, n] (workspace: 2 b doubles). */
+int sb_ign2to1_ops_factors(const float* V, int64_t ldv, int32_t n, const int32_t* col0, int32_t b, int32_t mult,
+                           float* ops, int32_t ldo, void* stream);
+int sb_ign2to1_ops_projectors(const float* P, int32_t n, int32_t b, float* ops, int32_t ldo, double* workspace,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -223,7 +223,7 @@ def run_b200(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -290,7 +290,7 @@ def run_reference(args):
     v = round(B * steps / dt, 2)
     sample = (f"{steps} timed steps (after warm-up) of fwd+bwd on {B} ZINC-shape graphs per step with the oracle port "
               f"of the reference (torch CPU fp32, all host threads)")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "graphs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(dt / steps * 1e3, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
@@ -298,7 +298,29 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout: library chatter written to fd 1 (e.g. NCCL's version banner) goes to
+    stderr instead; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
@@ -311,6 +333,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=64, help="graphs per step of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

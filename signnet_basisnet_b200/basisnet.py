@@ -1,4 +1,5 @@
-"""BasisNet's IGN phi on the B200 kernels: `IGN2to1` and `IGNBasisInv` of the single-graph LearningFilters tree.
+"""The single-graph LearningFilters tree on the B200 kernels: BasisNet's IGN phi (`IGN2to1`, `IGNBasisInv`) and the
+DeepSets SignNet (`SignPlus(EqDeepSetsEncoder)`).
 
 Mirrors LearningFilters/ign.py:9-39 (IGN2to1), :88-128 (layer_2_to_1), :174-214 (layer_1_to_1), :344-374 / :404-417
 (contractions) and LearningFilters/signbasisnet.py:23-41 (IGNBasisInv): same constructor arguments and state_dict keys
@@ -36,31 +37,34 @@ class _Segments:
         self.batch = torch.arange(b, device=device, dtype=torch.int64).repeat_interleave(n)
 
 
-class _SegBiasReluFn(torch.autograd.Function):
-    """out[e, i, :] = relu(t[e, i, :] + u[e, :]) on [b, n, ld] rows (the broadcast half of a 1->1 equivariant layer)."""
+class _SegBiasActFn(torch.autograd.Function):
+    """out[e, i, :] = act(t[e, i, :] + u[e, :]) on [b, n, ld] rows: the broadcast half of a 1->1 equivariant / DeepSets
+    layer (act = ReLU or identity)."""
 
     @staticmethod
-    def forward(ctx, t, u, seg, n, C):
+    def forward(ctx, t, u, seg, n, C, relu):
         t, u = t.contiguous(), u.contiguous()
         ld = t.shape[1]
         ones = torch.ones(seg.B, C, dtype=torch.float32, device=t.device)
         uc = u[:, :C].contiguous()
         out = torch.empty_like(t)
-        _call("sb_affine_act_res", _p(t), _p(ones), _p(uc), None, _p(out), ld, n, seg.B, C, 1)
-        ctx.save_for_backward(out)
-        ctx.cfg = (seg, C, u.shape)
+        _call("sb_affine_act_res", _p(t), _p(ones), _p(uc), None, _p(out), ld, n, seg.B, C, int(relu))
+        ctx.save_for_backward(out if relu else None)
+        ctx.cfg = (seg, C, u.shape, relu)
         return out
 
     @staticmethod
     def backward(ctx, g):
         (out,) = ctx.saved_tensors
-        seg, C, ushape = ctx.cfg
+        seg, C, ushape, relu = ctx.cfg
         g = g.contiguous()
-        gt = torch.empty_like(g)
-        _call("sb_relu_bwd", _p(g), _p(out), _p(gt), g.numel())
+        gt = g
+        if relu:
+            gt = torch.empty_like(g)
+            _call("sb_relu_bwd", _p(g), _p(out), _p(gt), g.numel())
         gu = torch.zeros(ushape, dtype=torch.float32, device=g.device)
         _call("sb_segment_pool_fwd", _p(gt), gt.stride(0), _p(seg.graph_ptr), seg.B, C, 0, _p(gu), gu.stride(0))
-        return gt, gu, None, None, None
+        return gt, gu, None, None, None, None
 
 
 class _EquiLayer(nn.Module):
@@ -134,7 +138,7 @@ class IGN2to1(nn.Module):
             t = linear(x, lyr.coeffs[:, :, 0].t(), None, pad4(S))
             xm = SegmentPoolFn.apply(x, seg, S, True)
             u = linear(xm, lyr.coeffs[:, :, 1].t(), lyr.bias.reshape(-1), pad4(S))
-            x = _SegBiasReluFn.apply(t, u, seg, n, S)
+            x = _SegBiasActFn.apply(t, u, seg, n, S, True)
             x = self._bn(x, i)
         x = linear(x, self.fc1.weight, self.fc1.bias, pad4(S), relu=True)
         return linear(x, self.fc2.weight, self.fc2.bias, pad4(self.out_channels))
@@ -169,6 +173,64 @@ class IGNBasisInv(nn.Module):
 
     def forward_factors(self, V, col0, mult):
         return self.encs[self.mult_to_idx[int(mult)]].forward_factors(V, col0, mult)
+
+
+class EqDeepSetsEncoder(nn.Module):
+    """Equivariant DeepSets encoder, `* x set size x feature size` (LearningFilters/models.py:58-113): phi and rho of the
+    single-graph SignNet (training.py:207-218).  Layer: act(lin1(x) + lin2(mean over the set)), BatchNorm1d with
+    track_running_stats=False (always batch statistics).  Same constructor and state_dict keys (lins1/lins2/bns)."""
+
+    def __init__(self, in_channels, hidden_channels=32, out_channels=1, num_layers=3, use_bn=False, use_ln=False,
+                 dropout=0.0, activation="relu"):
+        super().__init__()
+        if use_ln or activation != "relu":
+            raise NotImplementedError("EqDeepSetsEncoder on the B200 path: use_ln / non-ReLU activations are not built "
+                                      "(no reference configuration selects them)")
+        dims = [in_channels] + [hidden_channels] * (num_layers - 1) + [out_channels]
+        self.lins1 = nn.ModuleList(nn.Linear(dims[i], dims[i + 1]) for i in range(num_layers))
+        self.lins2 = nn.ModuleList(nn.Linear(dims[i], dims[i + 1]) for i in range(num_layers))
+        if use_bn:
+            self.bns = nn.ModuleList(nn.BatchNorm1d(hidden_channels, track_running_stats=False)
+                                     for _ in range(num_layers - 1))
+        self.use_bn, self.use_ln, self.dropout = use_bn, use_ln, dropout
+
+    def forward(self, x, *args):
+        if not (x.is_cuda and x.dtype == torch.float32):
+            raise ValueError("x must be a CUDA float32 tensor (no CPU fallback)")
+        if x.dim() not in (2, 3):
+            raise ValueError("invalid x dimension")
+        if self.dropout > 0 and self.training:
+            raise NotImplementedError("dropout > 0 is not built (every reference configuration uses 0.0)")
+        lead = x.shape[0] if x.dim() == 3 else 1
+        n, cin = x.shape[-2], x.shape[-1]
+        seg = _Segments(lead, n, x.device)
+        rows = x.reshape(lead * n, cin).contiguous()
+        L = len(self.lins1)
+        for i in range(L):
+            l1, l2 = self.lins1[i], self.lins2[i]
+            C = l1.out_features
+            t = linear(rows, l1.weight, l1.bias, pad4(C))
+            xm = SegmentPoolFn.apply(rows, seg, l1.in_features, True)
+            u = linear(xm, l2.weight, l2.bias, pad4(C))
+            last = i == L - 1
+            rows = _SegBiasActFn.apply(t, u, seg, n, C, not last)
+            if not last and self.use_bn:
+                rows = batch_norm_act(rows, self.bns[i], self.training, relu=False)
+        out = rows[:, :self.lins1[-1].out_features]
+        return out.reshape(lead, n, -1) if x.dim() == 3 else out
+
+
+class SignPlus(nn.Module):
+    """model(v) + model(-v); `x` (not negated) is concatenated on the feature dim (signbasisnet.py:11-20)."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+    def forward(self, v, *args, x=None):
+        if x is None:
+            return self.model(v) + self.model(-v)
+        return self.model(torch.cat((v, x), dim=-1)) + self.model(torch.cat((-v, x), dim=-1))
 
 
 def eigenspace_groups(eigvals: torch.Tensor, decimals: int = 5):

@@ -113,3 +113,41 @@ def test_ign_basis_inv_and_grouping():
         assert y.shape == (starts.numel(), m, 40) and torch.isfinite(y).all()
     with pytest.raises(ValueError):
         net.encs[0].ops_from_factors(V.cpu(), groups[1], 1)
+
+
+@pytest.mark.parametrize("shape,cin,hid,cout,L", [((8, 200, 1), 1, 32, 1, 3), ((200, 16), 16, 10, 32, 3), ((5, 37, 3), 3, 12, 4, 1)])
+def test_eq_deepsets_sign_plus_vs_oracle(shape, cin, hid, cout, L):
+    """cfg 1 (row a14): SignPlus(EqDeepSetsEncoder) = phi of the single-graph SignNet on [k, n, 1]; rho on [n, 2k]."""
+    from signnet_basisnet_b200.basisnet import EqDeepSetsEncoder, SignPlus
+
+    torch.manual_seed(shape[-2])
+    net = SignPlus(EqDeepSetsEncoder(cin, hid, cout, L, use_bn=True)).to(DEV).train()
+    with torch.no_grad():
+        for bn in getattr(net.model, "bns", []):
+            bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.2)
+
+    def leaves(dtype):
+        d = {k[len("model."):]: v.detach().cpu().to(dtype) for k, v in net.state_dict().items()}
+        for v in d.values():
+            v.requires_grad_(True)
+        return d
+
+    sd, sd64 = leaves(torch.float32), leaves(torch.float64)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(*shape, generator=g)
+    w = torch.randn(*shape[:-1], cout, generator=g)
+    ref = restate.sign_plus_deepsets(x, sd, "", L)
+    (ref * w).sum().backward()
+    ref64 = restate.sign_plus_deepsets(x.double(), sd64, "", L)
+    (ref64 * w.double()).sum().backward()
+    out = net(x.to(DEV))
+    (out * w.to(DEV)).sum().backward()
+    assert_parity(out, ref, ref64, 1e-5, what="SignPlus(EqDeepSets)")
+    got = {k[len("model."):]: p.grad.cpu() for k, p in net.named_parameters() if p.grad is not None}
+    g32 = {k: v.grad for k, v in sd.items() if v.grad is not None}
+    g64 = {k: v.grad for k, v in sd64.items() if v.grad is not None}
+    assert set(got) == set(g64)
+    assert_grads_parity(got, g32, g64, 2e-5, "SignPlus(EqDeepSets)")
+    # sign invariance (SURVEY section 4): f(v) == f(-v) up to the order of the fp64 statistics atomics
+    a, b2 = net(x.to(DEV)), net(-x.to(DEV))
+    assert (a - b2).abs().max() <= 1e-6 * a.abs().max()

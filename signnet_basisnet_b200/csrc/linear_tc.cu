@@ -125,9 +125,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
 
   // ---- one-time: split the weight into head/tail, canonical K-major SW128 blocks; rows >= N and columns >= K are 0
   for (int idx = tid; idx < nkb * 128 * TC_KB; idx += TC_THREADS) {
-    int n, k;
-    if (a.w_cs == 1) { n = idx / (nkb * TC_KB); k = idx - n * (nkb * TC_KB); }
-    else { k = idx / 128; n = idx - k * 128; }
+    // lanes run along k for either weight orientation: one 128-byte swizzle row per warp store = conflict-free.  (With
+    // lanes along n - the coalesced order for the transposed weight of the input-gradient launches - all 32 stores of a
+    // warp hit the same bank: 32-way conflicts cost ~10 % of such a launch; the strided global reads are L2 hits.)
+    const int n = idx / (nkb * TC_KB), k = idx - n * (nkb * TC_KB);
     float v = 0.f;
     if (k < K && n < N) v = __ldg(a.w + (long long)n * a.w_rs + (long long)k * a.w_cs);
     float h, l;

@@ -19,7 +19,8 @@
 #define WT_WORKERS 512
 #define WT_THREADS (WT_WORKERS + 32)
 #define WT_MAXG 2
-#define WT_L2_AHEAD 6   // chunks requested into L2 ahead of the register prefetch (cp.async.bulk.prefetch.L2)
+#define WT_SLOTS 3       // register prefetch depth in chunks (3 x 32 KB in flight per SM on top of the L2 prefetch)
+#define WT_L2_AHEAD 8   // chunks requested into L2 ahead of the register prefetch (cp.async.bulk.prefetch.L2)
 
 struct WgTcArgs {
   const float* g;
@@ -129,64 +130,65 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
   } else {
     // ================================================================================================== workers
     // item q of a thread: idx = tid + 512 q -> 32-feature block (idx >> 8), row (idx >> 3) & 31, float4 (idx & 7)
-    float4 pg0[2], pg1[2], px0[2], px1[2];   // two prefetch slots (selected with predicated moves, no local memory)
+    // WT_SLOTS register prefetch slots; the chunk loop is unrolled by WT_SLOTS so every slot index is a compile-time
+    // constant: a chunk waits only for ITS loads (issued WT_SLOTS chunks earlier).  The first version selected the slot
+    // with predicated moves, which made every chunk also wait for the loads issued one chunk earlier.
+    float4 pg[WT_SLOTS][2], px[WT_SLOTS][2];
     float dbs[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    auto load_chunk = [&](long long c, int slot) {
-      const int g = (c >= cpg) ? 1 : 0;   // G <= WT_MAXG = 2: no 64-bit division in the hot loop
-      const long long row0 = (c - (long long)g * cpg) * WT_ROWS;
-      const int rows = (int)((a.R - row0 < WT_ROWS) ? (a.R - row0) : WT_ROWS);
-      const long long base = (long long)g * a.R + row0;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int idx = tid + WT_WORKERS * q;
-        const int row = (idx >> 3) & 31, col = (idx >> 8) * 32 + (idx & 7) * 4;
-        float4 vg = make_float4(0.f, 0.f, 0.f, 0.f), vx = vg;
-        if (FAST) {
-          if (row < rows) {
-            vg = ldg4(a.g + (base + row) * a.ldg + col);
-            vx = ldg4(a.x + (base + row) * a.ldx + col);
-          }
-        } else if (row < rows) {
-          if (col < N) {
-            const float* p = a.g + (base + row) * a.ldg + col;
-            if (a.gvec) {
-              vg = ldg4(p);
-            } else {
-              vg.x = __ldg(p);
-              if (col + 1 < N) vg.y = __ldg(p + 1);
-              if (col + 2 < N) vg.z = __ldg(p + 2);
-              if (col + 3 < N) vg.w = __ldg(p + 3);
-            }
-          }
-          if (col < K) {
-            const float* p = a.x + (base + row) * a.ldx + col;
-            if (a.xvec) {
-              vx = ldg4(p);
-            } else {
-              vx.x = __ldg(p);
-              if (col + 1 < K) vx.y = __ldg(p + 1);
-              if (col + 2 < K) vx.z = __ldg(p + 2);
-              if (col + 3 < K) vx.w = __ldg(p + 3);
-            }
-          }
-        }
-        if (slot) { pg1[q] = vg; px1[q] = vx; } else { pg0[q] = vg; px0[q] = vx; }
-      }
-    };
-    auto store_chunk = [&](int stage, int slot, long long c) {
-      const int g = (c >= cpg) ? 1 : 0;   // G <= WT_MAXG = 2: no 64-bit division in the hot loop
+    const int row = (tid >> 3) & 31, c4 = tid & 7;
+#define WT_LOAD(CC, S)                                                                         \
+    {                                                                                          \
+      const long long c_ = (CC);                                                               \
+      const int g_ = (c_ >= cpg) ? 1 : 0; /* G <= WT_MAXG = 2: no 64-bit division */           \
+      const long long row0_ = (c_ - (long long)g_ * cpg) * WT_ROWS;                            \
+      const int rows_ = (int)((a.R - row0_ < WT_ROWS) ? (a.R - row0_) : WT_ROWS);              \
+      const long long base_ = (long long)g_ * a.R + row0_;                                     \
+      _Pragma("unroll") for (int q = 0; q < 2; ++q) {                                          \
+        const int col = ((tid + WT_WORKERS * q) >> 8) * 32 + c4 * 4;                           \
+        float4 vg = make_float4(0.f, 0.f, 0.f, 0.f), vx = vg;                                  \
+        if (FAST) {                                                                            \
+          if (row < rows_) {                                                                   \
+            vg = ldg4(a.g + (base_ + row) * a.ldg + col);                                      \
+            vx = ldg4(a.x + (base_ + row) * a.ldx + col);                                      \
+          }                                                                                    \
+        } else if (row < rows_) {                                                              \
+          if (col < N) {                                                                       \
+            const float* p = a.g + (base_ + row) * a.ldg + col;                                \
+            if (a.gvec) vg = ldg4(p);                                                          \
+            else {                                                                             \
+              vg.x = __ldg(p);                                                                 \
+              if (col + 1 < N) vg.y = __ldg(p + 1);                                            \
+              if (col + 2 < N) vg.z = __ldg(p + 2);                                            \
+              if (col + 3 < N) vg.w = __ldg(p + 3);                                            \
+            }                                                                                  \
+          }                                                                                    \
+          if (col < K) {                                                                       \
+            const float* p = a.x + (base_ + row) * a.ldx + col;                                \
+            if (a.xvec) vx = ldg4(p);                                                          \
+            else {                                                                             \
+              vx.x = __ldg(p);                                                                 \
+              if (col + 1 < K) vx.y = __ldg(p + 1);                                            \
+              if (col + 2 < K) vx.z = __ldg(p + 2);                                            \
+              if (col + 3 < K) vx.w = __ldg(p + 3);                                            \
+            }                                                                                  \
+          }                                                                                    \
+        }                                                                                      \
+        pg[S][q] = vg;                                                                         \
+        px[S][q] = vx;                                                                         \
+      }                                                                                        \
+    }
+    auto store_chunk = [&](int stage, const float4 (&vgs)[2], const float4 (&vxs)[2], long long c) {
+      const int g = (c >= cpg) ? 1 : 0;
       const long long row0 = (c - (long long)g * cpg) * WT_ROWS;
       const int rows = (int)((a.R - row0 < WT_ROWS) ? (a.R - row0) : WT_ROWS);
       uint8_t* sb = ring + stage * WT_STAGE_BYTES;
+      const bool live = row < rows;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const int idx = tid + WT_WORKERS * q;
-        const int row = (idx >> 3) & 31, blk = idx >> 8, c4 = idx & 7;
+        const int blk = (tid + WT_WORKERS * q) >> 8;
         const int col = blk * 32 + c4 * 4;
-        const bool live = row < rows;
-        const float4 vg = slot ? pg1[q] : pg0[q], vx = slot ? px1[q] : px0[q];
-        float tg[4] = {vg.x, vg.y, vg.z, vg.w};
-        float tx[4] = {vx.x, vx.y, vx.z, vx.w};
+        float tg[4] = {vgs[q].x, vgs[q].y, vgs[q].z, vgs[q].w};
+        float tx[4] = {vxs[q].x, vxs[q].y, vxs[q].z, vxs[q].w};
         if (a.pro) {   // coefficients of columns >= K are (1, 0): harmless, those entries are zeroed below
           const float4 pa4 = *reinterpret_cast<const float4*>(&s_pa[g * 128 + col]);
           const float4 pc4 = *reinterpret_cast<const float4*>(&s_pc[g * 128 + col]);
@@ -217,7 +219,6 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
         *reinterpret_cast<float4*>(sb + 3 * WT_BLK_BYTES + off) = l;
       }
     };
-
     // one thread asks L2 for a whole chunk (rows are contiguous: 32 x ld floats per operand)
     const bool l2ok = FAST || (a.gvec && a.xvec);
     auto l2_chunk = [&](long long cc) {
@@ -231,27 +232,35 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
     long long c = blockIdx.x;
     unsigned cnt = 0;
     if (tid == 32 && l2ok)
-      for (int s = 2; s < WT_L2_AHEAD; ++s)
+      for (int s = WT_SLOTS; s < WT_L2_AHEAD; ++s)
         if (c + (long long)s * gridDim.x < nch) l2_chunk(c + (long long)s * gridDim.x);
-    if (c < nch) load_chunk(c, 0);
-    if (c + gridDim.x < nch) load_chunk(c + gridDim.x, 1);
-    for (; c < nch; c += gridDim.x, ++cnt) {
-      const int stage = cnt % WT_STAGES;
-      const unsigned use = cnt / WT_STAGES;
-      if (use > 0) mbar_wait(&mma_done[stage], (use - 1) & 1);
-      const int slot = cnt & 1;
-      store_chunk(stage, slot, c);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[stage]);   // one arrival per worker warp: no block-wide barrier per chunk
-      if (tid == 32 && l2ok) {
-        const long long cl = c + (long long)WT_L2_AHEAD * gridDim.x;
-        if (cl < nch) l2_chunk(cl);
+#pragma unroll
+    for (int s = 0; s < WT_SLOTS; ++s)
+      if (c + (long long)s * gridDim.x < nch) WT_LOAD(c + (long long)s * gridDim.x, s)
+    while (c < nch) {
+#pragma unroll
+      for (int s = 0; s < WT_SLOTS; ++s) {
+        if (c < nch) {   // CTA-uniform
+          const int stage = cnt % WT_STAGES;
+          const unsigned use = cnt / WT_STAGES;
+          if (use > 0) mbar_wait(&mma_done[stage], (use - 1) & 1);
+          store_chunk(stage, pg[s], px[s], c);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[stage]);   // one arrival per worker warp: no block-wide barrier per chunk
+          if (tid == 32 && l2ok) {
+            const long long cl = c + (long long)WT_L2_AHEAD * gridDim.x;
+            if (cl < nch) l2_chunk(cl);
+          }
+          const long long cn = c + (long long)WT_SLOTS * gridDim.x;   // refill the slot just consumed
+          if (cn < nch) WT_LOAD(cn, s)
+          c += gridDim.x;
+          ++cnt;
+        }
       }
-      const long long c2 = c + 2ll * gridDim.x;   // the slot just consumed is refilled two chunks ahead
-      if (c2 < nch) load_chunk(c2, slot);
     }
+#undef WT_LOAD
 
     // ---- epilogue: accumulator -> per-CTA partial (row n per thread, 32 columns per warp)
     mbar_wait(&acc_done, 0);

@@ -133,8 +133,27 @@ def run_b200(args):
             sync.allreduce()
         return loss
 
+    # End to end: every step copies ITS batch host -> device from pinned memory (on a copy stream, issued one step ahead
+    # like a prefetching DataLoader would, so the transfer overlaps the previous step's backward) and reads the loss back.
+    copy_stream = torch.cuda.Stream(device=dev)
+    pending = []
+
+    def fetch():
+        with torch.cuda.stream(copy_stream):
+            d = host.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        pending.append((d, ev))
+
     def step_e2e():
-        data = host.to(dev, non_blocking=True)
+        if not pending:
+            fetch()
+        data, ev = pending.pop(0)
+        torch.cuda.current_stream().wait_event(ev)
+        for v in data.__dict__.values():
+            if torch.is_tensor(v):
+                v.record_stream(torch.cuda.current_stream())
+        fetch()  # next step's batch
         return float(step(data).item())  # D2H read of the loss
 
     def barrier():

@@ -93,6 +93,27 @@ def make_dgl():
     torch.save(out, os.path.join(OUT, "dgl_deepsigns.pt"))
 
 
+def make_gin_net():
+    """Row a13: the reference's own GINNet (+ its masked_gin sign_inv_net) on a small seeded batch."""
+    gn = ref_loader.gin_net()
+    import dgl
+    params = dict(num_atom_type=28, num_bond_type=4, hidden_dim=20, out_dim=20, in_feat_dropout=0.0, dropout=0.0, L=3,
+                  readout="mean", batch_norm=True, residual=True, edge_feat=False, device="cpu", pe_init="lap_pe",
+                  lap_method="sign_inv", lap_lspe=False, use_lapeig_loss=False, lambda_loss=0.0, alpha_loss=0.0,
+                  pos_enc_dim=6, sign_inv_net="masked_gin", phi_out_dim=8, sign_inv_layers=3, sign_inv_activation="relu")
+    torch.manual_seed(7)
+    net = gn.GINNet(params)
+    d = synth_batch(6, "zinc", seed=13, k_dgl=params["pos_enc_dim"])
+    g = dgl.BatchedGraph(d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph)
+    sd0 = _sd(net)
+    pe = net.sign_inv_net(g, d.pos_enc.unsqueeze(-1)).squeeze(-1)
+    out, _ = net(g, d.x[:, 0], pe, torch.ones(d.edge_index.shape[1], 1), None)
+    w = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
+    (out * w).sum().backward()
+    torch.save({"params": params, "state_dict": sd0, "data": _data_dict(d), "w": w, "out": out.detach(),
+                "grads": _grads(net)}, os.path.join(OUT, "dgl_gin_net.pt"))
+
+
 def make_ign():
     ign, _ = ref_loader.learningfilters()
     torch.manual_seed(3)
@@ -109,6 +130,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     make_alchemy()
     make_dgl()
+    make_gin_net()
     make_ign()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

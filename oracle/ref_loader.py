@@ -72,6 +72,13 @@ def graphprediction_layers():
     return ds, importlib.import_module("layers.gnns"), importlib.import_module("layers.mlp")
 
 
+def gin_net():
+    """-> nets.ZINC_graph_regression.gin_net of /root/reference/GraphPrediction (DGL GINNet predictor, row a13)."""
+    _ensure(_SHIM)
+    _ensure(os.path.join(REF_ROOT, "GraphPrediction"))
+    return importlib.import_module("nets.ZINC_graph_regression.gin_net")
+
+
 def learningfilters():
     """-> (ign, signbasisnet) of /root/reference/LearningFilters (torch only; construct with device='cpu')."""
     _ensure(os.path.join(REF_ROOT, "LearningFilters"))

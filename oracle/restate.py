@@ -318,6 +318,26 @@ def masked_gin_deepsigns(x, src, dst, num_nodes_per_graph, sd, n_layers, k, trai
     return h.reshape(x.shape[0], k, 1)
 
 
+def gin_net(h_idx, pos_enc, src, dst, num_nodes_per_graph, sd, n_layers, readout="mean", training=True, p=""):
+    """GINNet.forward, `pe_init='lap_pe'`, no LSPE (GraphPrediction/nets/ZINC_graph_regression/gin_net.py:81-138):
+    h = embedding_h(atom) + embedding_p(pos_enc); L x dgl GINConv(MLP(2 layers), 'sum'); mean/sum readout; MLPReadout
+    (layers/mlp_readout_layer.py:9-25).  embedding_e is computed and discarded by the reference (GINConv takes no e)."""
+    h = sd[p + "embedding_h.weight"][h_idx] + F.linear(pos_enc, sd[p + "embedding_p.weight"], sd[p + "embedding_p.bias"])
+    for l in range(n_layers):
+        eps = sd.get(f"{p}layers.{l}.eps", torch.zeros(1))
+        rst = (1 + eps) * h + torch.zeros_like(h).index_add_(0, dst, h.index_select(0, src))
+        h = dgl_mlp(rst, sd, f"{p}layers.{l}.apply_func.", 2, training)
+    n = torch.as_tensor(num_nodes_per_graph)
+    seg = torch.repeat_interleave(torch.arange(n.numel()), n)
+    hg = torch.zeros(n.numel(), h.shape[1], dtype=h.dtype).index_add_(0, seg, h)
+    if readout != "sum":
+        hg = hg / n.to(h.dtype).clamp(min=1).unsqueeze(1)
+    y, L = hg, 2
+    for l in range(L):
+        y = _relu(F.linear(y, sd[f"{p}MLP_layer.FC_layers.{l}.weight"], sd[f"{p}MLP_layer.FC_layers.{l}.bias"]))
+    return F.linear(y, sd[f"{p}MLP_layer.FC_layers.{L}.weight"], sd[f"{p}MLP_layer.FC_layers.{L}.bias"])
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # LearningFilters flavour (rows a14, a15): single-graph SignNet (DeepSets phi) and BasisNet IGN 2->1
 # --------------------------------------------------------------------------------------------------------------------

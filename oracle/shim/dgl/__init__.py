@@ -12,6 +12,7 @@ class BatchedGraph:
     def __init__(self, src, dst, num_nodes_per_graph):
         self.src, self.dst = src, dst
         self._bnn = torch.as_tensor(num_nodes_per_graph)
+        self.ndata, self.edata = {}, {}
 
     def edges(self):
         return self.src, self.dst
@@ -21,3 +22,27 @@ class BatchedGraph:
 
     def num_nodes(self):
         return int(self._bnn.sum())
+
+
+def _segments(g):
+    n = g.batch_num_nodes()
+    return torch.repeat_interleave(torch.arange(n.numel()), n), n
+
+
+def sum_nodes(g, key):
+    """dgl.sum_nodes: per-graph sum of a node feature (gin_net.py:127-134 readout)."""
+    seg, n = _segments(g)
+    x = g.ndata[key]
+    return torch.zeros(n.numel(), *x.shape[1:], dtype=x.dtype).index_add_(0, seg, x)
+
+
+def mean_nodes(g, key):
+    seg, n = _segments(g)
+    s = sum_nodes(g, key)
+    return s / n.to(s.dtype).clamp(min=1).reshape(-1, *([1] * (s.dim() - 1)))
+
+
+def max_nodes(g, key):
+    seg, n = _segments(g)
+    x = g.ndata[key]
+    return torch.stack([x[seg == b].max(0).values for b in range(n.numel())])

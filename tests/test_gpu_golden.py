@@ -101,3 +101,23 @@ def test_dgl_deepsigns_golden(golden_dir, name):
             assert_close_rel(net.state_dict()[k_].cpu(), v, 2e-5, what=k_)
         elif "num_batches" in k_:
             assert torch.equal(net.state_dict()[k_].cpu(), v), k_
+
+
+def test_gin_net_golden(golden_dir):
+    """Row a13: GINNet(net_params) with its sign_inv_net on the GPU vs the reference's own output and gradients."""
+    from signnet_basisnet_b200.gin_net import GINNet
+
+    g = _load(golden_dir, "dgl_gin_net.pt")
+    d, prm = Data(**g["data"]).to(DEV), dict(g["params"], device=DEV)
+    net = GINNet(prm).to(DEV).train()
+    assert set(net.state_dict()) == set(g["state_dict"])
+    net.load_state_dict(g["state_dict"])
+    G = _G(d)
+    pe = net.sign_inv_net(G, d.pos_enc.unsqueeze(-1)).squeeze(-1)       # handle_lap, train_ZINC_graph_regression.py:20-25
+    out, g_ret = net(G, d.x[:, 0], pe, torch.ones(d.edge_index.shape[1], 1, device=DEV), None)
+    assert g_ret is G and out.shape == g["out"].shape
+    assert_close_rel(out.cpu(), g["out"], 2e-5, what="GINNet vs reference")
+    (out * g["w"].to(DEV)).sum().backward()
+    got = {k: p.grad.cpu() for k, p in net.named_parameters() if p.grad is not None}
+    assert set(got) == set(g["grads"])
+    assert_grads_close(got, g["grads"], 1e-4, "GINNet vs reference")

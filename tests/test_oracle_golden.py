@@ -80,3 +80,18 @@ def test_ign2to1_golden(golden_dir):
     g = _load(golden_dir, "ign2to1.pt")
     sd = {k: v.clone() for k, v in g["state_dict"].items()}
     assert_close_rel(restate.ign2to1(g["P"], sd), g["out"], 1e-5, what="IGN2to1")
+
+
+def test_gin_net_golden(golden_dir):
+    """Row a13: oracle restatement of the DGL GINNet predictor (+ its masked_gin sign_inv_net) vs the reference's output."""
+    g = _load(golden_dir, "dgl_gin_net.pt")
+    d, prm = Data(**g["data"]), g["params"]
+    sd = _leaf(g["state_dict"])
+    sub = {k[len("sign_inv_net."):]: v for k, v in sd.items() if k.startswith("sign_inv_net.")}
+    pe = restate.masked_gin_deepsigns(d.pos_enc.unsqueeze(-1), d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph, sub,
+                                      prm["sign_inv_layers"], prm["pos_enc_dim"]).squeeze(-1)
+    out = restate.gin_net(d.x[:, 0], pe, d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph, sd, prm["L"],
+                          prm["readout"])
+    assert_close_rel(out, g["out"], 2e-5, what="GINNet")
+    (out * g["w"]).sum().backward()
+    assert_grads_close({k: v.grad for k, v in sd.items() if not k.endswith(".eps")}, g["grads"], 5e-5, "GINNet")

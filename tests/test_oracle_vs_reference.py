@@ -111,3 +111,40 @@ def test_ign2to1():
     V = torch.linalg.qr(torch.randn(20, 6))[0]
     P = torch.stack([V[:, :2] @ V[:, :2].T, V[:, 2:4] @ V[:, 2:4].T, V[:, 4:6] @ V[:, 4:6].T]).unsqueeze(1)
     torch.testing.assert_close(restate.ign2to1(P, sd), net(P), rtol=1e-5, atol=1e-6)
+
+
+GIN_NET_PARAMS = dict(num_atom_type=28, num_bond_type=4, hidden_dim=20, out_dim=20, in_feat_dropout=0.0, dropout=0.0, L=3,
+                      readout="mean", batch_norm=True, residual=True, edge_feat=False, device="cpu", pe_init="lap_pe",
+                      lap_method="sign_inv", lap_lspe=False, use_lapeig_loss=False, lambda_loss=0.0, alpha_loss=0.0,
+                      pos_enc_dim=6, sign_inv_net="masked_gin", phi_out_dim=8, sign_inv_layers=3,
+                      sign_inv_activation="relu")
+
+
+@pytest.mark.parametrize("readout", ["mean", "sum"])
+def test_gin_net_predictor(readout):
+    """Row a13: the DGL GINNet predictor consuming the sign-invariant PE (gin_net.py:81-138, handle_lap :20-25)."""
+    gn = ref_loader.gin_net()   # puts the stand-in dgl on sys.path
+    import dgl
+
+    torch.manual_seed(5)
+    params = dict(GIN_NET_PARAMS, readout=readout)
+    net = gn.GINNet(params)
+    k = params["pos_enc_dim"]
+    d = synth_batch(6, "zinc", seed=12, k_dgl=k)
+    g = dgl.BatchedGraph(d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph)
+    sd = _leafify(_clone_sd(net))
+    atoms = d.x[:, 0]
+    pe = net.sign_inv_net(g, d.pos_enc.unsqueeze(-1)).squeeze(-1)          # handle_lap, train_ZINC_graph_regression.py:20-25
+    ref, _ = net(g, atoms, pe, torch.ones(d.edge_index.shape[1], 1), None)
+    pe_o = restate.masked_gin_deepsigns(d.pos_enc.unsqueeze(-1), d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph,
+                                        {k2[len("sign_inv_net."):]: v for k2, v in sd.items() if k2.startswith("sign_inv_net.")},
+                                        params["sign_inv_layers"], k).squeeze(-1)
+    out = restate.gin_net(atoms, pe_o, d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph, sd, params["L"], readout)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-5)
+    w = torch.randn_like(ref)
+    (ref * w).sum().backward()
+    (out * w).sum().backward()
+    want = {k2: v.grad for k2, v in net.named_parameters() if v.grad is not None}
+    got = {k2: v.grad for k2, v in sd.items() if v.requires_grad and v.grad is not None and not k2.endswith(".eps")}
+    assert set(want) == set(got)   # dgl GINConv eps is a buffer; embedding_e never reaches the output (no gradient)
+    assert_grads_close(got, want, 5e-5, "gin_net")

@@ -134,7 +134,8 @@ int sb_bn_finalize(const double* stats, int64_t M, int32_t G, int32_t C, const f
 /* out = act(pa*y + pc) + res  (GNN3d tail: norm -> relu -> residual, sign_net.py:40-43) */
 int sb_affine_act_res(const float* y, const float* pa, const float* pc, const float* res, float* out, int64_t ld,
                       int64_t R, int32_t G, int32_t C, int32_t relu, void* stream);
-/* backward of act(BN(y)): dz = gout*[pa*y+pc > 0]; stats[G,2,C] += (sum dz, sum dz*y_hat) in fp64 */
+/* backward of act(BN(y)): dz = gout*[pa*y+pc > 0] (written only if dz != NULL); stats[G,2,C] += (sum dz, sum dz*y_hat)
+ * in fp64 */
 int sb_bn_bwd_reduce(const float* gout, const float* y, const float* pa, const float* pc, const double* mean_rstd,
                      float* dz, int64_t ld, int64_t R, int32_t G, int32_t C, int32_t relu, double* stats,
                      void* stream);
@@ -142,8 +143,10 @@ int sb_bn_bwd_reduce(const float* gout, const float* y, const float* pa, const f
 int sb_bn_bwd_finalize(const double* stats, int64_t M, int32_t G, int32_t C, const float* gamma,
                        const double* mean_rstd, int32_t training, int32_t accumulate, float* dgamma, float* dbeta,
                        double* coef, void* stream);
-int sb_affine2(const float* t1, const float* t2, const double* coef, const double* mean_rstd, float* out, int64_t ld,
-               int64_t R, int32_t G, int32_t C, void* stream);
+/* out = al*dz + be*(t2 - mean) + ga with dz = t1, or dz = t1 * [pa*t2 + pc > 0] when pa/pc are given (the ReLU mask
+ * of the forward recomputed here, so sb_bn_bwd_reduce need not write dz: one activation-sized write less per BN). */
+int sb_affine2(const float* t1, const float* t2, const double* coef, const double* mean_rstd, const float* pa,
+               const float* pc, float* out, int64_t ld, int64_t R, int32_t G, int32_t C, void* stream);
 
 int sb_relu_bwd(const float* g, const float* y, float* out, int64_t n, void* stream); /* out = g * [y > 0] */
 

@@ -34,7 +34,7 @@ _SIGNATURES = {
     "sb_affine_act_res": "ppppp" + "ll" + "iii" + "p",
     "sb_bn_bwd_reduce": "pppppp" + "ll" + "iii" + "p" + "p",
     "sb_bn_bwd_finalize": "pl" + "ii" + "pp" + "ii" + "ppp" + "p",
-    "sb_affine2": "ppppp" + "ll" + "ii" + "p",
+    "sb_affine2": "ppppppp" + "ll" + "ii" + "p",
     "sb_gine_agg_fwd": "pppppp" + "li" + "p" + "p",
     "sb_gine_agg_bwd": "pppp" + "pppp" + "lli" + "ppp" + "p",
     "sb_segment_pool_fwd": "plp" + "iii" + "pl" + "p",

@@ -181,7 +181,7 @@ extern "C" int sb_affine_act_res(const float* y, const float* pa, const float* p
 // --------------------------------------------------------------------------- backward: relu mask + BN reductions
 // dz = gout * [a*y + c > 0]  (relu) or gout;  s1[g,c] += sum_r dz ;  s2[g,c] += sum_r dz * (y - mean) * rstd.
 // dz may alias gout (in place).
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const float* gout, const float* __restrict__ y,
+__global__ void __launch_bounds__(EW_THREADS, 3) bn_bwd_reduce_kernel(const float* gout, const float* __restrict__ y,
                                                                    const float* __restrict__ pa,
                                                                    const float* __restrict__ pc,
                                                                    const double* __restrict__ mean_rstd, float* dz,
@@ -207,22 +207,36 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const float* 
       m4[j] = ok ? mean_rstd[(long long)g * C + col] : 0.0;
       r4[j] = ok ? mean_rstd[((long long)G + g) * C + col] : 0.0;
     }
-    for (long long r = (long long)blockIdx.x * rpi + rs; r < R; r += (long long)gridDim.x * rpi) {
-      const long long off = ((long long)g * R + r) * ld + cg * 4;
-      const float4 gv = *reinterpret_cast<const float4*>(gout + off);
-      const float4 yv = ldg4(y + off);
-      const float gi[4] = {gv.x, gv.y, gv.z, gv.w}, yi[4] = {yv.x, yv.y, yv.z, yv.w};
-      float o[4];
+    const long long rstep = (long long)gridDim.x * rpi;
+    // two rows per thread and iteration in flight (pure stream: bytes in flight are what buys HBM bandwidth)
+    for (long long r0 = (long long)blockIdx.x * rpi + rs; r0 < R; r0 += 2 * rstep) {
+      const long long rr[2] = {r0, r0 + rstep};
+      float4 gv2[2], yv2[2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float d = gi[j];
-        if (relu && !(fmaf(a4[j], yi[j], c4[j]) > 0.f)) d = 0.f;
-        if (cg * 4 + j >= C) d = 0.f;
-        o[j] = d;
-        s1[j] += (double)d;
-        s2[j] += (double)d * (((double)yi[j] - m4[j]) * r4[j]);
+      for (int i = 0; i < 2; ++i) {
+        if (rr[i] < R) {
+          const long long off = ((long long)g * R + rr[i]) * ld + cg * 4;
+          gv2[i] = *reinterpret_cast<const float4*>(gout + off);
+          yv2[i] = ldg4(y + off);
+        }
       }
-      if (dz) *reinterpret_cast<float4*>(dz + off) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (rr[i] >= R) break;
+        const long long off = ((long long)g * R + rr[i]) * ld + cg * 4;
+        const float gi[4] = {gv2[i].x, gv2[i].y, gv2[i].z, gv2[i].w}, yi[4] = {yv2[i].x, yv2[i].y, yv2[i].z, yv2[i].w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float d = gi[j];
+          if (relu && !(fmaf(a4[j], yi[j], c4[j]) > 0.f)) d = 0.f;
+          if (cg * 4 + j >= C) d = 0.f;
+          o[j] = d;
+          s1[j] += (double)d;
+          s2[j] += (double)d * (((double)yi[j] - m4[j]) * r4[j]);
+        }
+        if (dz) *reinterpret_cast<float4*>(dz + off) = make_float4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
   const int W = ldv * 4;
@@ -320,67 +334,100 @@ __device__ __forceinline__ F2 split_d(double v) {
   r.lo = (float)(v - (double)r.hi);
   return r;
 }
-__global__ void __launch_bounds__(EW_THREADS) affine2_kernel(const float* t1, const float* __restrict__ t2,
+__global__ void __launch_bounds__(EW_THREADS, 4) affine2_kernel(const float* t1, const float* __restrict__ t2,
                                                              const double* __restrict__ coef,
-                                                             const double* __restrict__ mean_rstd, float* out,
-                                                             long long ld, long long R, int G, int C) {
-  // tab[k][g*ld + col], k = (al.hi, al.lo, be.hi, be.lo, ga.hi, ga.lo, mu.hi, mu.lo): fp64 -> float pairs once per
-  // block (not per element); structure-of-arrays so a warp's float4 reads are conflict-free.
+                                                             const double* __restrict__ mean_rstd,
+                                                             const float* __restrict__ pa,
+                                                             const float* __restrict__ pc, float* out, long long ld,
+                                                             long long R, int G, int C) {
+  // tab[k][g*ld + col], k = (al.hi, al.lo, be.hi, be.lo, ga.hi, ga.lo, mu.hi, mu.lo, pa, pc): fp64 -> float pairs once
+  // per block (not per element); structure-of-arrays so a warp's float4 reads are conflict-free.
   extern __shared__ __align__(16) float tab[];
   const long long GC = (long long)G * C;
   const int GL = G * (int)ld;
+  const bool mask = pa != nullptr;   // t1 is the upstream gradient: apply the ReLU mask [pa*t2 + pc > 0] here
   for (int p = threadIdx.x; p < GL; p += blockDim.x) {
     const int g = p / (int)ld, col = p - g * (int)ld;
     F2 al = {0.f, 0.f}, be = al, ga = al, mu = al;
+    float a_ = 0.f, c_ = 0.f;
     if (col < C) {
       const long long q = (long long)g * C + col;
       al = split_d(coef[q]); be = split_d(coef[GC + q]); ga = split_d(coef[2 * GC + q]); mu = split_d(mean_rstd[q]);
+      if (mask) { a_ = __ldg(pa + q); c_ = __ldg(pc + q); }
     }
     tab[0 * GL + p] = al.hi; tab[1 * GL + p] = al.lo; tab[2 * GL + p] = be.hi; tab[3 * GL + p] = be.lo;
     tab[4 * GL + p] = ga.hi; tab[5 * GL + p] = ga.lo; tab[6 * GL + p] = mu.hi; tab[7 * GL + p] = mu.lo;
+    tab[8 * GL + p] = a_; tab[9 * GL + p] = c_;
   }
   __syncthreads();
   const long long ld4 = ld >> 2;
   const long long total = (long long)G * R * ld4;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const long long row = t / ld4;
-    const int c4 = (int)(t - row * ld4);
-    const int g = (int)(row / R);
-    const float4 u = *reinterpret_cast<const float4*>(t1 + t * 4);
-    const float4 v = ldg4(t2 + t * 4);
-    const int p = g * (int)ld + c4 * 4;
-    float4 k[8];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // two independent float4 items per thread and iteration: 64 B of loads in flight per thread (the kernel is a pure
+  // stream; with one item it sat at ~70 % of the HBM peak for lack of bytes in flight at 3 CTAs / SM)
+  for (long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; t0 < total; t0 += 2 * stride) {
+    const long long tt[2] = {t0, t0 + stride};
+    float4 uu[2], vv[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) k[i] = *reinterpret_cast<const float4*>(tab + i * GL + p);
-    float4 o;
-#define SB_AFF2(c)                                                                 \
-    {                                                                              \
-      const float d = (v.c - k[6].c) - k[7].c;      /* t2 - mean */                \
-      float acc = fmaf(k[3].c, d, k[5].c);          /* be.lo * d + ga.lo */        \
-      acc = fmaf(k[1].c, u.c, acc);                 /* + al.lo * t1 */             \
-      acc = fmaf(k[2].c, d, acc + k[4].c);          /* + be.hi * d + ga.hi */      \
-      o.c = fmaf(k[0].c, u.c, acc);                 /* + al.hi * t1 */             \
+    for (int i = 0; i < 2; ++i) {
+      if (tt[i] < total) {
+        uu[i] = *reinterpret_cast<const float4*>(t1 + tt[i] * 4);
+        vv[i] = ldg4(t2 + tt[i] * 4);
+      }
     }
-    SB_AFF2(x) SB_AFF2(y) SB_AFF2(z) SB_AFF2(w)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (tt[i] >= total) break;
+      const long long t = tt[i];
+      const long long row = t / ld4;
+      const int c4 = (int)(t - row * ld4);
+      const int g = (row >= R) ? (int)(row / R) : 0;
+      float4 u = uu[i];
+      const float4 v = vv[i];
+      const int p = g * (int)ld + c4 * 4;
+      float4 k[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) k[q] = *reinterpret_cast<const float4*>(tab + q * GL + p);
+      if (mask) {   // same predicate as bn_bwd_reduce_kernel: dz = gout * [pa*y + pc > 0]
+        const float4 a4 = *reinterpret_cast<const float4*>(tab + 8 * GL + p);
+        const float4 c4v = *reinterpret_cast<const float4*>(tab + 9 * GL + p);
+        if (!(fmaf(a4.x, v.x, c4v.x) > 0.f)) u.x = 0.f;
+        if (!(fmaf(a4.y, v.y, c4v.y) > 0.f)) u.y = 0.f;
+        if (!(fmaf(a4.z, v.z, c4v.z) > 0.f)) u.z = 0.f;
+        if (!(fmaf(a4.w, v.w, c4v.w) > 0.f)) u.w = 0.f;
+      }
+      float4 o;
+#define SB_AFF2(c)                                                                 \
+      {                                                                            \
+        const float d = (v.c - k[6].c) - k[7].c;      /* t2 - mean */              \
+        float acc = fmaf(k[3].c, d, k[5].c);          /* be.lo * d + ga.lo */      \
+        acc = fmaf(k[1].c, u.c, acc);                 /* + al.lo * t1 */           \
+        acc = fmaf(k[2].c, d, acc + k[4].c);          /* + be.hi * d + ga.hi */    \
+        o.c = fmaf(k[0].c, u.c, acc);                 /* + al.hi * t1 */           \
+      }
+      SB_AFF2(x) SB_AFF2(y) SB_AFF2(z) SB_AFF2(w)
 #undef SB_AFF2
-    // padding columns: every table entry is 0 there, so o = 0 as required
-    *reinterpret_cast<float4*>(out + t * 4) = o;
+      // padding columns: every table entry is 0 there, so o = 0 as required
+      *reinterpret_cast<float4*>(out + t * 4) = o;
+    }
   }
 }
 
-extern "C" int sb_affine2(const float* t1, const float* t2, const double* coef, const double* mean_rstd, float* out,
-                          int64_t ld, int64_t R, int32_t G, int32_t C, void* stream) {
+extern "C" int sb_affine2(const float* t1, const float* t2, const double* coef, const double* mean_rstd,
+                          const float* pa, const float* pc, float* out, int64_t ld, int64_t R, int32_t G, int32_t C,
+                          void* stream) {
   SB_CHECK_ARG(ld % 4 == 0 && ld >= C && G >= 1, "sb_affine2: ld must be a multiple of 4 and >= C");
+  SB_CHECK_ARG((pa == nullptr) == (pc == nullptr), "sb_affine2: pa/pc must come together");
   if (R == 0) return SB_OK;
   const long long total = (long long)G * R * (ld / 4);
   long long blocks = sb_ceil_div(total, EW_THREADS * 4);
   const long long cap = (long long)sb_num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  const size_t smem = (size_t)G * ld * 8 * sizeof(float);
+  const size_t smem = (size_t)G * ld * 10 * sizeof(float);
   SB_CHECK_ARG(smem <= 48 * 1024, "sb_affine2: G*ld too large");
-  affine2_kernel<<<(unsigned)blocks, EW_THREADS, smem, (cudaStream_t)stream>>>(t1, t2, coef, mean_rstd, out, ld, R, G, C);
+  affine2_kernel<<<(unsigned)blocks, EW_THREADS, smem, (cudaStream_t)stream>>>(t1, t2, coef, mean_rstd, pa, pc, out, ld,
+                                                                              R, G, C);
   SB_CHECK_LAUNCH("sb_affine2");
   return SB_OK;
 }

@@ -244,17 +244,44 @@ __global__ void embedding_bwd_reduce_kernel(const float* __restrict__ partial, i
   for (int p = 0; p < nparts; ++p) s += partial[(long long)p * V * C + t];
   dtable[t] = s;
 }
-// Large vocabularies (table does not fit shared memory): fp32 atomics into a zeroed table.
-__global__ void embedding_bwd_atomic_kernel(const int64_t* __restrict__ idx, long long stride,
-                                            const float* __restrict__ g, long long ldg, int V, int C, long long M,
-                                            float* __restrict__ dtable) {
+// Large vocabularies (table does not fit shared memory): fp32 atomics into a zeroed table.  Categorical features use
+// few distinct values (28 atom / 4 bond types inside DiscreteEncoder's 500-row tables, elements.py:22-25), so rows
+// v < EMB_HOT are privatised per CTA in shared memory (shared-memory atomics, then one global atomic per touched
+// element and CTA) instead of ~1000-way contended global atomics; colder rows still go straight to global memory.
+#define EMB_HOT 64
+__global__ void __launch_bounds__(256) embedding_bwd_atomic_kernel(const int64_t* __restrict__ idx, long long stride,
+                                                                    const float* __restrict__ g, long long ldg, int V,
+                                                                    int C, long long M, int hot_rows,
+                                                                    float* __restrict__ dtable) {
+  extern __shared__ float hot[];          // [hot_rows <= EMB_HOT][C]
+  __shared__ unsigned long long used;     // bit v: row v < EMB_HOT was touched by this CTA
+  const int hotn = hot_rows * C;
+  for (int i = threadIdx.x; i < hotn; i += blockDim.x) hot[i] = 0.f;
+  if (threadIdx.x == 0) used = 0ull;
+  __syncthreads();
   const long long total = M * C;
+  unsigned long long mine = 0ull;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     const long long m = t / C;
     const int c = (int)(t - m * C);
     const long long v = idx[m * stride];
-    if (v >= 0 && v < V) atomicAdd(dtable + v * C + c, __ldg(g + m * ldg + c));
+    if (v >= 0 && v < V) {
+      const float x = __ldg(g + m * ldg + c);
+      if (v < hot_rows) {
+        atomicAdd(hot + v * C + c, x);
+        mine |= 1ull << v;
+      } else {
+        atomicAdd(dtable + v * C + c, x);
+      }
+    }
+  }
+  if (mine) atomicOr(&used, mine);
+  __syncthreads();
+  const unsigned long long u = used;
+  for (int i = threadIdx.x; i < hotn; i += blockDim.x) {
+    const int v = i / C;
+    if ((u >> v) & 1ull) atomicAdd(dtable + i, hot[i]);
   }
 }
 extern "C" int64_t sb_embedding_bwd_workspace_floats(int32_t V, int32_t C) {
@@ -269,10 +296,21 @@ extern "C" int sb_embedding_bwd(const int64_t* idx, int64_t stride, const float*
   if (M == 0 || smem > 200 * 1024) {
     SB_CUDA(cudaMemsetAsync(dtable, 0, sizeof(float) * V * C, st));
     if (M == 0) return SB_OK;
-    long long blocks = sb_ceil_div(M * C, 256);
-    const long long cap = (long long)sb_num_sms() * 16;
+    long long blocks = sb_ceil_div(M * C, 256 * 8);
+    const long long cap = (long long)sb_num_sms() * 2;
     if (blocks > cap) blocks = cap;
-    embedding_bwd_atomic_kernel<<<(unsigned)blocks, 256, 0, st>>>(idx, stride, g, ldg, V, C, M, dtable);
+    if (blocks < 1) blocks = 1;
+    int hot_rows = (int)((160 * 1024) / ((size_t)C * sizeof(float)));
+    if (hot_rows > EMB_HOT) hot_rows = EMB_HOT;
+    const size_t hot_smem = (size_t)hot_rows * C * sizeof(float);
+    static size_t configured = 0;
+    if (hot_smem > configured) {
+      SB_CUDA(cudaFuncSetAttribute(embedding_bwd_atomic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)hot_smem));
+      configured = hot_smem;
+    }
+    embedding_bwd_atomic_kernel<<<(unsigned)blocks, 256, hot_smem, st>>>(idx, stride, g, ldg, V, C, M, hot_rows,
+                                                                           dtable);
     SB_CHECK_LAUNCH("sb_embedding_bwd(atomic)");
     return SB_OK;
   }

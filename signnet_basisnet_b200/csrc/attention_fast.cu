@@ -303,28 +303,255 @@ __global__ void __launch_bounds__(32 * AF_WARPS_B) attention_fast_bwd_kernel(con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// v2 (16-byte aligned head slices): only the two tiles a phase broadcasts live in shared memory - K, V while a lane is
+// a query, Q, dO while a lane is a key - and the lane's own rows come straight from global memory into registers.
+// Shared memory per warp drops from 22.4 / 33.8 KB to 16.5 / 21.6 KB, i.e. 12 / 10 instead of 8 / 6 resident warps per
+// SM for a kernel that is bound by the latency of its dependent FMA chains (profiles/r1h_launches_step.csv: 4.6 ms for
+// 2 GB of traffic and 18 GFLOP).
+__device__ __forceinline__ void af_row_global(float* r, const float* __restrict__ src, int dk4) {
+#pragma unroll
+  for (int c4 = 0; c4 < AF_DK / 4; ++c4) {
+    float4 k = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < dk4) k = ldg4(src + c4 * 4);
+    r[c4 * 4 + 0] = k.x; r[c4 * 4 + 1] = k.y; r[c4 * 4 + 2] = k.z; r[c4 * 4 + 3] = k.w;
+  }
+}
+#define AF2_FWD_FLOATS (2 * AF_KMAX * AF_LDS + AF_KMAX * 32)
+#define AF2_BWD_FLOATS (2 * AF_KMAX * AF_LDS + 2 * AF_KMAX * 32 + 3 * AF_KMAX)
+
+// DK4 > 0: head width fixed at compile time (dk = 4 * DK4) - no per-FMA predicates; DK4 = 0: runtime width.
+// Loop bodies are kept small on purpose: the first v2 build unrolled the (j1, j2) loops four times and spent 36 % of
+// its issue slots waiting for instruction fetch (21 KB loop body, profiles/r1j_att_bwd_ncu.csv).
+template <int DK4>
+__global__ void __launch_bounds__(32 * AF_WARPS) attention_fast2_fwd_kernel(const AttArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const AfCtx c = af_ctx<AF_WARPS>(a);
+  if (!c.active) return;
+  const int dk4 = DK4 > 0 ? DK4 : c.dk4;
+  float* Ks = sm + (size_t)warp * AF2_FWD_FLOATS;
+  float* Vs = Ks + AF_KMAX * AF_LDS;
+  float* Ss = Vs + AF_KMAX * AF_LDS;   // [j2][lane] score scratch of this warp
+  af_load_async(a.k, a.ld, c, Ks);
+  af_load_async(a.v, a.ld, c, Vs);
+  const long long node = blockIdx.x;
+  float q[AF_DK];
+  if (lane < c.kb) af_row_global(q, a.q + (c.r0 + (long long)lane * c.n) * a.ld + c.h * c.dk, dk4);
+  af_async_wait();   // every lane: its own cp.async group, then the warp barrier that publishes the tiles
+  for (int j1 = lane; j1 < c.kb; j1 += 32) {
+    if (j1 != lane) af_row_global(q, a.q + (c.r0 + (long long)j1 * c.n) * a.ld + c.h * c.dk, dk4);
+#pragma unroll
+    for (int cc = 0; cc < AF_DK; ++cc) q[cc] = __fdiv_rn(q[cc], a.inv_temp_div);
+    float m = -INFINITY;
+#pragma unroll 2
+    for (int j2 = 0; j2 < c.kb; ++j2) {
+      const float sc = af_dot(q, Ks + j2 * AF_LDS, dk4);
+      Ss[j2 * 32 + lane] = sc;
+      m = fmaxf(m, sc);
+    }
+    float o[AF_DK];
+#pragma unroll
+    for (int cc = 0; cc < AF_DK; ++cc) o[cc] = 0.f;
+    float sum = 0.f;
+    for (int j2 = 0; j2 < c.kb; ++j2) {   // pass 2a: row sum (the reference normalises before dropout and P V)
+      const float e = expf(Ss[j2 * 32 + lane] - m);
+      Ss[j2 * 32 + lane] = e;
+      sum += e;
+    }
+#pragma unroll 2
+    for (int j2 = 0; j2 < c.kb; ++j2) {
+      float p = __fdiv_rn(Ss[j2 * 32 + lane], sum);
+      if (a.drop_p > 0.f) p *= att_keep_scale(a.seed, node, c.h, j1, j2, a.drop_p);
+      af_axpy(o, p, Vs + j2 * AF_LDS, dk4);
+    }
+    float* dst = a.o + (c.r0 + (long long)j1 * c.n) * a.ld + c.h * c.dk;
+#pragma unroll
+    for (int c4 = 0; c4 < AF_DK / 4; ++c4)
+      if (c4 < dk4)
+        *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(o[c4 * 4], o[c4 * 4 + 1], o[c4 * 4 + 2], o[c4 * 4 + 3]);
+  }
+}
+
+template <int DK4>
+__global__ void __launch_bounds__(32 * AF_WARPS_B, 4) attention_fast2_bwd_kernel(const AttArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const AfCtx c = af_ctx<AF_WARPS_B>(a);
+  if (!c.active) return;
+  const int dk4 = DK4 > 0 ? DK4 : c.dk4;
+  float* T0 = sm + (size_t)warp * AF2_BWD_FLOATS;   // K, then Q
+  float* T1 = T0 + AF_KMAX * AF_LDS;                // V, then dO
+  float* Ps = T1 + AF_KMAX * AF_LDS;                // [j2][lane] probabilities (phase A scratch)
+  float* Dp = Ps + AF_KMAX * 32;                    // [j2][lane] dP            (phase A scratch)
+  float* Ms = Dp + AF_KMAX * 32;                    // row max
+  float* Ls = Ms + AF_KMAX;                         // row sum
+  float* Ds = Ls + AF_KMAX;                         // sum_j2 dP * P
+  af_load_async(a.k, a.ld, c, T0);
+  af_load_async(a.v, a.ld, c, T1);
+  const long long node = blockIdx.x;
+  // ---- phase A: lane = query j1 -> row statistics, D, dQ   (K, V tiles in shared memory; q, dO rows in registers)
+  {
+    float q[AF_DK], g[AF_DK];
+    if (lane < c.kb) {
+      const long long roff0 = (c.r0 + (long long)lane * c.n) * a.ld + c.h * c.dk;
+      af_row_global(q, a.q + roff0, dk4);
+      af_row_global(g, a.go + roff0, dk4);
+    }
+    af_async_wait();   // every lane: its own cp.async group, then the warp barrier that publishes the tiles
+  for (int j1 = lane; j1 < c.kb; j1 += 32) {
+    const long long roff = (c.r0 + (long long)j1 * c.n) * a.ld + c.h * c.dk;
+    if (j1 != lane) {
+      af_row_global(q, a.q + roff, dk4);
+      af_row_global(g, a.go + roff, dk4);
+    }
+#pragma unroll
+    for (int cc = 0; cc < AF_DK; ++cc) q[cc] = __fdiv_rn(q[cc], a.inv_temp_div);
+    float m = -INFINITY;
+#pragma unroll 2
+    for (int j2 = 0; j2 < c.kb; ++j2) {
+      const float sc = af_dot(q, T0 + j2 * AF_LDS, dk4);
+      Ps[j2 * 32 + lane] = sc;
+      m = fmaxf(m, sc);
+    }
+    float sum = 0.f;
+    for (int j2 = 0; j2 < c.kb; ++j2) {
+      const float e = expf(Ps[j2 * 32 + lane] - m);
+      Ps[j2 * 32 + lane] = e;
+      sum += e;
+    }
+    float dot = 0.f;
+#pragma unroll 2
+    for (int j2 = 0; j2 < c.kb; ++j2) {
+      float dp = af_dot(g, T1 + j2 * AF_LDS, dk4);
+      if (a.drop_p > 0.f) dp *= att_keep_scale(a.seed, node, c.h, j1, j2, a.drop_p);
+      const float p = __fdiv_rn(Ps[j2 * 32 + lane], sum);
+      Ps[j2 * 32 + lane] = p;
+      Dp[j2 * 32 + lane] = dp;
+      dot = fmaf(dp, p, dot);
+    }
+    float dq[AF_DK];
+#pragma unroll
+    for (int cc = 0; cc < AF_DK; ++cc) dq[cc] = 0.f;
+#pragma unroll 2
+    for (int j2 = 0; j2 < c.kb; ++j2) {
+      const float ds = Ps[j2 * 32 + lane] * (Dp[j2 * 32 + lane] - dot);
+      af_axpy(dq, ds, T0 + j2 * AF_LDS, dk4);
+    }
+    Ms[j1] = m;
+    Ls[j1] = sum;
+    Ds[j1] = dot;
+    float* dst = a.gq + roff;
+#pragma unroll
+    for (int c4 = 0; c4 < AF_DK / 4; ++c4)
+      if (c4 < dk4)
+        *reinterpret_cast<float4*>(dst + c4 * 4) =
+            make_float4(__fdiv_rn(dq[c4 * 4], a.inv_temp_div), __fdiv_rn(dq[c4 * 4 + 1], a.inv_temp_div),
+                        __fdiv_rn(dq[c4 * 4 + 2], a.inv_temp_div), __fdiv_rn(dq[c4 * 4 + 3], a.inv_temp_div));
+  }
+  }
+  __syncwarp();
+  // ---- phase B: lane = key j2 -> dK, dV (P and dS recomputed column-wise from Q, K and the row statistics).
+  // The two tiles are refilled with Q and dO; the lane's own K / V rows come from global memory.
+  af_load_async(a.q, a.ld, c, T0);
+  af_load_async(a.go, a.ld, c, T1);
+  float kr[AF_DK], vr[AF_DK];
+  if (lane < c.kb) {
+    const long long roff0 = (c.r0 + (long long)lane * c.n) * a.ld + c.h * c.dk;
+    af_row_global(kr, a.k + roff0, dk4);
+    af_row_global(vr, a.v + roff0, dk4);
+  }
+  af_async_wait();
+  af_scale_rows(T0, c, a.inv_temp_div);   // all lanes: q / temperature, as the forward used it
+  for (int j2 = lane; j2 < c.kb; j2 += 32) {
+    float dk_[AF_DK], dv_[AF_DK];
+    const long long roff = (c.r0 + (long long)j2 * c.n) * a.ld + c.h * c.dk;
+    if (j2 != lane) {
+      af_row_global(kr, a.k + roff, dk4);
+      af_row_global(vr, a.v + roff, dk4);
+    }
+#pragma unroll
+    for (int cc = 0; cc < AF_DK; ++cc) { dk_[cc] = 0.f; dv_[cc] = 0.f; }
+#pragma unroll 1
+    for (int j1 = 0; j1 < c.kb; ++j1) {
+      const float sc = af_dot(kr, T0 + j1 * AF_LDS, dk4);
+      float dp = af_dot(vr, T1 + j1 * AF_LDS, dk4);
+      const float p = __fdiv_rn(expf(sc - Ms[j1]), Ls[j1]);
+      float pd = p;
+      if (a.drop_p > 0.f) {
+        const float ks = att_keep_scale(a.seed, node, c.h, j1, j2, a.drop_p);
+        pd *= ks;
+        dp *= ks;
+      }
+      const float ds = p * (dp - Ds[j1]);
+      af_axpy(dv_, pd, T1 + j1 * AF_LDS, dk4);
+      af_axpy(dk_, ds, T0 + j1 * AF_LDS, dk4);
+    }
+    float* dstk = a.gk + roff;
+    float* dstv = a.gv + roff;
+#pragma unroll
+    for (int c4 = 0; c4 < AF_DK / 4; ++c4) {
+      if (c4 < dk4) {
+        *reinterpret_cast<float4*>(dstk + c4 * 4) = make_float4(dk_[c4 * 4], dk_[c4 * 4 + 1], dk_[c4 * 4 + 2], dk_[c4 * 4 + 3]);
+        *reinterpret_cast<float4*>(dstv + c4 * 4) = make_float4(dv_[c4 * 4], dv_[c4 * 4 + 1], dv_[c4 * 4 + 2], dv_[c4 * 4 + 3]);
+      }
+    }
+  }
+}
+
+static bool af_vec_host(const AttArgs& a) {
+  auto al = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
+  return (a.dk & 3) == 0 && (a.ld & 3) == 0 && al(a.q) && al(a.k) && al(a.v) && al(a.o);
+}
 int sb_attention_fast_fwd_launch(const AttArgs& a, int kmax, cudaStream_t st) {
   if (kmax > AF_KMAX || a.dk > AF_DK) return SB_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)a.N, (unsigned)((a.n_head + AF_WARPS - 1) / AF_WARPS));
+  if (af_vec_host(a)) {
+    const size_t smem2 = (size_t)AF_WARPS * AF2_FWD_FLOATS * sizeof(float);
+    static bool configured2 = false;
+    if (!configured2) {
+      SB_CUDA(cudaFuncSetAttribute(attention_fast2_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      SB_CUDA(cudaFuncSetAttribute(attention_fast2_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      configured2 = true;
+    }
+    if (a.dk == 32) attention_fast2_fwd_kernel<8><<<grid, 32 * AF_WARPS, smem2, st>>>(a);
+    else attention_fast2_fwd_kernel<0><<<grid, 32 * AF_WARPS, smem2, st>>>(a);
+    SB_CHECK_LAUNCH("sb_attention_fwd(fast2)");
+    return SB_OK;
+  }
   const size_t smem = (size_t)AF_WARPS * (3 * AF_KMAX * AF_LDS + AF_KMAX * 32) * sizeof(float);
   static bool configured = false;
   if (!configured) {
     SB_CUDA(cudaFuncSetAttribute(attention_fast_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((unsigned)a.N, (unsigned)((a.n_head + AF_WARPS - 1) / AF_WARPS));
   attention_fast_fwd_kernel<<<grid, 32 * AF_WARPS, smem, st>>>(a);
   SB_CHECK_LAUNCH("sb_attention_fwd(fast)");
   return SB_OK;
 }
 int sb_attention_fast_bwd_launch(const AttArgs& a, int kmax, cudaStream_t st) {
   if (kmax > AF_KMAX || a.dk > AF_DK) return SB_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)a.N, (unsigned)((a.n_head + AF_WARPS_B - 1) / AF_WARPS_B));
+  auto al = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
+  if ((a.dk & 3) == 0 && (a.ld & 3) == 0 && al(a.q) && al(a.k) && al(a.v) && al(a.go) && al(a.gq) && al(a.gk) && al(a.gv)) {
+    const size_t smem2 = (size_t)AF_WARPS_B * AF2_BWD_FLOATS * sizeof(float);
+    static bool configured2 = false;
+    if (!configured2) {
+      SB_CUDA(cudaFuncSetAttribute(attention_fast2_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      SB_CUDA(cudaFuncSetAttribute(attention_fast2_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      configured2 = true;
+    }
+    if (a.dk == 32) attention_fast2_bwd_kernel<8><<<grid, 32 * AF_WARPS_B, smem2, st>>>(a);
+    else attention_fast2_bwd_kernel<0><<<grid, 32 * AF_WARPS_B, smem2, st>>>(a);
+    SB_CHECK_LAUNCH("sb_attention_bwd(fast2)");
+    return SB_OK;
+  }
   const size_t smem = (size_t)AF_WARPS_B * (4 * AF_KMAX * AF_LDS + 2 * AF_KMAX * 32 + 3 * AF_KMAX) * sizeof(float);
   static bool configured = false;
   if (!configured) {
     SB_CUDA(cudaFuncSetAttribute(attention_fast_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((unsigned)a.N, (unsigned)((a.n_head + AF_WARPS_B - 1) / AF_WARPS_B));
   attention_fast_bwd_kernel<<<grid, 32 * AF_WARPS_B, smem, st>>>(a);
   SB_CHECK_LAUNCH("sb_attention_bwd(fast)");
   return SB_OK;

@@ -25,7 +25,8 @@ class AttentionFn(torch.autograd.Function):
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         gi = slots.gi
         ld = q.shape[1]
-        o = torch.zeros_like(q)
+        # every slot row belongs to exactly one node: the kernel writes all of o unless there are padding columns
+        o = torch.empty_like(q) if n_head * dk == ld else torch.zeros_like(q)
         temp = float(dk) ** 0.5
         _call("sb_attention_fwd", _p(q), _p(k), _p(v), ld, _p(gi.batch), _p(gi.graph_ptr), _p(slots.row_ptr), gi.N,
               slots.k, int(slots.masked), max(slots.kmax, 1), n_head, dk, temp, float(drop_p), int(seed), _p(o))
@@ -39,7 +40,8 @@ class AttentionFn(torch.autograd.Function):
         slots, n_head, dk, temp, drop_p, seed = ctx.cfg
         gi = slots.gi
         go = go.contiguous()
-        gq, gk, gv = torch.zeros_like(q), torch.zeros_like(q), torch.zeros_like(q)
+        alloc = torch.empty_like if n_head * dk == q.shape[1] else torch.zeros_like
+        gq, gk, gv = alloc(q), alloc(q), alloc(q)
         _call("sb_attention_bwd", _p(q), _p(k), _p(v), _p(go), q.shape[1], _p(gi.batch), _p(gi.graph_ptr),
               _p(slots.row_ptr), gi.N, slots.k, int(slots.masked), max(slots.kmax, 1), n_head, dk, temp, drop_p, seed,
               _p(gq), _p(gk), _p(gv))

@@ -225,13 +225,15 @@ def test_linear_wgrad(K, N, pro, R=777):
 
 @pytest.mark.parametrize("K,N,pro,relu,bias", [(1, 128, 0, False, False), (1, 64, 1, True, True), (1, 95, 2, False, True),
                                                (128, 1, 0, False, False), (95, 1, 2, True, True),
-                                               (128, 128, 2, False, True), (64, 128, 0, True, False)])
+                                               (128, 128, 2, False, True), (64, 128, 0, True, False),
+                                               (95, 95, 1, True, True), (96, 70, 2, False, True), (20, 128, 0, False, False)])
 def test_linear_fwd_streaming_sizes(K, N, pro, relu, bias):
     """Row counts above the small-problem threshold: the rank-1 / row-dot kernels of the first phi layer
     (csrc/linear_rank1.cu) and the tcgen05 path (csrc/linear_tc.cu), including a ragged last tile."""
     test_linear_fwd_and_stats(K, N, pro, relu, bias, R=2999)
 
 
-@pytest.mark.parametrize("K,N,pro", [(1, 128, 0), (1, 64, 2), (1, 95, 1), (128, 128, 2)])
+@pytest.mark.parametrize("K,N,pro", [(1, 128, 0), (1, 64, 2), (1, 95, 1), (128, 128, 2), (95, 95, 1), (64, 128, 0),
+                                     (70, 96, 2)])
 def test_linear_wgrad_streaming_sizes(K, N, pro):
     test_linear_wgrad(K, N, pro, R=2999)

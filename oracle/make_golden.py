@@ -114,6 +114,23 @@ def make_gin_net():
                 "grads": _grads(net)}, os.path.join(OUT, "dgl_gin_net.pt"))
 
 
+def make_eq_deepsets():
+    """Row a14: the reference's own SignPlus(EqDeepSetsEncoder) (phi on [k, n, 1] and rho on [n, 2k], training.py:207-218)."""
+    models = ref_loader.learningfilters_models()
+    _, sbn = ref_loader.learningfilters()
+    out = {}
+    for name, shape, (cin, hid, cout, L) in (("phi", (8, 40, 1), (1, 32, 1, 3)), ("rho", (40, 16), (16, 10, 32, 3))):
+        torch.manual_seed(11)
+        net = sbn.SignPlus(models.EqDeepSetsEncoder(cin, hid, cout, L, use_bn=True))
+        x = torch.randn(*shape)
+        y = net(x)
+        w = torch.randn(y.shape, generator=torch.Generator().manual_seed(2))
+        (y * w).sum().backward()
+        out[name] = {"cfg": dict(cin=cin, hid=hid, cout=cout, L=L), "state_dict": _sd(net), "x": x, "w": w,
+                     "out": y.detach(), "grads": _grads(net)}
+    torch.save(out, os.path.join(OUT, "eq_deepsets.pt"))
+
+
 def make_ign():
     ign, _ = ref_loader.learningfilters()
     torch.manual_seed(3)
@@ -131,6 +148,7 @@ if __name__ == "__main__":
     make_alchemy()
     make_dgl()
     make_gin_net()
+    make_eq_deepsets()
     make_ign()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -79,6 +79,14 @@ def gin_net():
     return importlib.import_module("nets.ZINC_graph_regression.gin_net")
 
 
+def learningfilters_models():
+    """-> LearningFilters/models.py (EqDeepSetsEncoder, row a14), imported unmodified; needs the PyG stand-ins because
+    the file also defines spectral-GNN baselines that are off the hot path."""
+    _ensure(_SHIM)
+    _ensure(os.path.join(REF_ROOT, "LearningFilters"))
+    return importlib.import_module("models")
+
+
 def learningfilters():
     """-> (ign, signbasisnet) of /root/reference/LearningFilters (torch only; construct with device='cpu')."""
     _ensure(os.path.join(REF_ROOT, "LearningFilters"))

@@ -78,7 +78,7 @@ class _Unused(torch.nn.Module):
         raise NotImplementedError("off the SignNet hot path")
 
 
-GATConv = GCNConv = _Unused
+GATConv = GCNConv = ARMAConv = ChebConv = APPNP = _Unused   # baselines of LearningFilters/models.py: import-only
 
 
 def global_add_pool(x, batch, size=None):

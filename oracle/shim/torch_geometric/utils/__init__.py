@@ -39,3 +39,13 @@ def get_laplacian(edge_index, edge_weight=None, normalization=None, dtype=None, 
         ei = torch.cat([torch.stack([row, col]), torch.stack([loop, loop])], 1)
         return ei, torch.cat([-(dinv[row] * w), torch.ones(n, dtype=w.dtype)])
     raise ValueError(normalization)
+
+
+def add_self_loops(edge_index, edge_weight=None, fill_value=1.0, num_nodes=None):
+    """Import-only for LearningFilters/models.py; semantics of PyG 2.0.1 restated for completeness."""
+    n = int(edge_index.max()) + 1 if num_nodes is None else num_nodes
+    loop = torch.arange(n, dtype=edge_index.dtype)
+    ei = torch.cat([edge_index, torch.stack([loop, loop])], dim=1)
+    if edge_weight is not None:
+        edge_weight = torch.cat([edge_weight, edge_weight.new_full((n,), fill_value)])
+    return ei, edge_weight

@@ -121,3 +121,21 @@ def test_gin_net_golden(golden_dir):
     got = {k: p.grad.cpu() for k, p in net.named_parameters() if p.grad is not None}
     assert set(got) == set(g["grads"])
     assert_grads_close(got, g["grads"], 1e-4, "GINNet vs reference")
+
+
+@pytest.mark.parametrize("name", ["phi", "rho"])
+def test_eq_deepsets_golden(golden_dir, name):
+    """Row a14: SignPlus(EqDeepSetsEncoder) on the GPU vs the reference's own output and gradients."""
+    from signnet_basisnet_b200.basisnet import EqDeepSetsEncoder, SignPlus
+
+    m = _load(golden_dir, "eq_deepsets.pt")[name]
+    c = m["cfg"]
+    net = SignPlus(EqDeepSetsEncoder(c["cin"], c["hid"], c["cout"], c["L"], use_bn=True)).to(DEV).train()
+    assert set(net.state_dict()) == set(m["state_dict"])
+    net.load_state_dict(m["state_dict"])
+    out = net(m["x"].to(DEV))
+    assert_close_rel(out.cpu(), m["out"], 2e-5, what=f"SignPlus(EqDeepSets) {name} vs reference")
+    (out * m["w"].to(DEV)).sum().backward()
+    got = {k: p.grad.cpu() for k, p in net.named_parameters() if p.grad is not None}
+    assert set(got) == set(m["grads"])
+    assert_grads_close(got, m["grads"], 1e-4, f"SignPlus(EqDeepSets) {name} vs reference")

@@ -95,3 +95,13 @@ def test_gin_net_golden(golden_dir):
     assert_close_rel(out, g["out"], 2e-5, what="GINNet")
     (out * g["w"]).sum().backward()
     assert_grads_close({k: v.grad for k, v in sd.items() if not k.endswith(".eps")}, g["grads"], 5e-5, "GINNet")
+
+
+@pytest.mark.parametrize("name", ["phi", "rho"])
+def test_eq_deepsets_golden(golden_dir, name):
+    m = _load(golden_dir, "eq_deepsets.pt")[name]
+    sd = _leaf({k[len("model."):]: v for k, v in m["state_dict"].items()})
+    out = restate.sign_plus_deepsets(m["x"], sd, "", m["cfg"]["L"])
+    assert_close_rel(out, m["out"], 1e-5, what=f"SignPlus(EqDeepSets) {name}")
+    (out * m["w"]).sum().backward()
+    assert_grads_close({k: v.grad for k, v in sd.items()}, {k[len("model."):]: v for k, v in m["grads"].items()}, 2e-5, name)

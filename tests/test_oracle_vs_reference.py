@@ -148,3 +148,24 @@ def test_gin_net_predictor(readout):
     got = {k2: v.grad for k2, v in sd.items() if v.requires_grad and v.grad is not None and not k2.endswith(".eps")}
     assert set(want) == set(got)   # dgl GINConv eps is a buffer; embedding_e never reaches the output (no gradient)
     assert_grads_close(got, want, 5e-5, "gin_net")
+
+
+@pytest.mark.parametrize("shape,cin,hid,cout,L", [((8, 50, 1), 1, 32, 1, 3), ((50, 16), 16, 10, 32, 3), ((4, 9, 3), 3, 6, 2, 1)])
+def test_eq_deepsets_sign_plus(shape, cin, hid, cout, L):
+    """Row a14: SignPlus(EqDeepSetsEncoder) of the single-graph SignNet (signbasisnet.py:11-20, models.py:58-113)."""
+    models = ref_loader.learningfilters_models()
+    _, sbn = ref_loader.learningfilters()
+    torch.manual_seed(4)
+    net = sbn.SignPlus(models.EqDeepSetsEncoder(cin, hid, cout, L, use_bn=True))
+    sd = _leafify({k[len("model."):]: v for k, v in _clone_sd(net).items()})
+    x = torch.randn(*shape)
+    ref = net(x)
+    out = restate.sign_plus_deepsets(x, sd, "", L)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
+    w = torch.randn_like(ref)
+    (ref * w).sum().backward()
+    (out * w).sum().backward()
+    want = {k[len("model."):]: v.grad for k, v in net.named_parameters() if v.grad is not None}
+    got = {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
+    assert set(want) == set(got)
+    assert_grads_close(got, want, 2e-5, "eq_deepsets")

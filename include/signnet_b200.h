@@ -198,6 +198,14 @@ int sb_layernorm_fwd(const float* a, const float* b, const float* w, const float
 int sb_layernorm_bwd(const float* g, const float* x, const float* stat, const float* w, int64_t ld, int64_t R,
                      int32_t C, float* dx, double* dwb, void* stream);
 
+/* ---- K8: batched Laplacian eigendecomposition (the step before the path) -------------------
+ * Per graph: L = I - D^-1/2 A D^-1/2 (A symmetrised, de-duplicated, no self loops; isolated nodes D^-1/2 := 0) from the
+ * CSR by destination, diagonalised by a warp-per-graph parallel cyclic Jacobi (n_b <= 64).  eigen_values[N] ascending
+ * per graph, eigen_vectors[sum n_b^2] row-major V[node, eig] at vec_ptr[b] - the layout EVDTransform('sym') produces
+ * with torch.linalg.eigh on the CPU (Alchemy/sign_net/transform.py:7-23).  flags bit 0: a graph exceeded nmax. */
+int sb_laplacian_evd(const int32_t* graph_ptr, const int32_t* in_ptr, const int32_t* in_src, const int64_t* vec_ptr,
+                     int32_t B, int32_t nmax, float* eigen_values, float* eigen_vectors, int32_t* flags, void* stream);
+
 /* ---- K9: BasisNet IGN phi (LearningFilters/ign.py:344-374 contractions_2_to_1, normalization 'inf') ------------------
  * ops[(e*n + i)*ldo + 0..4] = { P_ii, tr(P)/n, sum_j P_ij/n, sum_j P_ji/n, sum_ij P_ij/n^2 } of the eigenspace projectors
  * P_e = V_e V_e^T, columns 5..ldo-1 zero.  _factors reads only the eigenvector blocks V[:, col0[e] .. col0[e]+mult)

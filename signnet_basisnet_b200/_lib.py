@@ -46,6 +46,7 @@ _SIGNATURES = {
     "sb_layernorm_fwd": "pppp" + "ll" + "i" + "f" + "ppp" + "p",
     "sb_layernorm_bwd": "pppp" + "ll" + "i" + "pp" + "p",
     "sb_relu_bwd": "pppl" + "p",
+    "sb_laplacian_evd": "pppp" + "ii" + "ppp" + "p",
     "sb_ign2to1_ops_factors": "plipiipi" + "p",
     "sb_ign2to1_ops_projectors": "piipip" + "p",
     "sb_slot_sum_fwd": "pll" + "i" + "ppp" + "l" + "iii" + "pl" + "i" + "p",

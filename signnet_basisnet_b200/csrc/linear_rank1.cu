@@ -183,17 +183,21 @@ __global__ void __launch_bounds__(R1_THREADS) rank1_wgrad_kernel(const R1WgArgs 
   }
 }
 
-// fixed-order fp64 sum of the per-block partials
+// fp64 sum of the per-block partials: a warp per output element (lanes stride the partials, fixed shuffle tree), so the
+// reduction over ~1200 CTAs is 37 dependent loads deep instead of 1184
 __global__ void rank1_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int N, float* __restrict__ dw,
                                           long long dw_stride, float* __restrict__ db, int accumulate) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 2 * N) return;
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (idx >= 2 * N) return;   // warp-uniform
   const int which = idx / N, n = idx - which * N;
   if (which == 1 && !db) return;
   double t = 0.0;
-  for (int p = 0; p < nparts; ++p) t += (double)part[((size_t)p * 2 + which) * 128 + n];
-  float* dst = which ? db + n : dw + n * dw_stride;
-  *dst = accumulate ? *dst + (float)t : (float)t;
+  for (int p = lane; p < nparts; p += 32) t += (double)part[((size_t)p * 2 + which) * 128 + n];
+  t = warp_sum_d(t);
+  if (lane == 0) {
+    float* dst = which ? db + n : dw + n * dw_stride;
+    *dst = accumulate ? *dst + (float)t : (float)t;
+  }
 }
 
 // ---- host entry points (called from linear.cu; SB_ERR_UNSUPPORTED = use the generic path) ----------------------------
@@ -242,7 +246,7 @@ int sb_rank1_wgrad_launch(const float* gy, int64_t ldg, const float* x, int64_t 
   const int grid = sb_num_sms() * 8;   // 2 * 128 floats per block: well inside sb_linear_wgrad_workspace_floats()
   rank1_wgrad_kernel<<<grid, R1_THREADS, 0, st>>>(a);
   SB_CHECK_LAUNCH("sb_linear_wgrad(rank1)");
-  rank1_wgrad_reduce_kernel<<<(2 * N + 127) / 128, 128, 0, st>>>(workspace, grid, N, dw, dw_rs, db, accumulate);
+  rank1_wgrad_reduce_kernel<<<(2 * N * 32 + 127) / 128, 128, 0, st>>>(workspace, grid, N, dw, dw_rs, db, accumulate);
   SB_CHECK_LAUNCH("sb_linear_wgrad(rank1 reduce)");
   return SB_OK;
 }

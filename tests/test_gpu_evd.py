@@ -89,3 +89,29 @@ def test_evd_feeds_signnet_like_the_cpu_transform():
         sg.__dict__.pop("_b200_graph_index", None)
         out = model(sg)
     assert (out - ref).abs().max() <= 2e-3 * ref.abs().max()
+
+
+def test_lap_positional_encoding_dgl_convention():
+    """DGL tree (molecules.py:148-181): trivial eigenvector dropped, next k kept, zero padded; columns match the CPU
+    eigh up to sign wherever the eigenvalue is isolated."""
+    from signnet_basisnet_b200.ops import lap_positional_encoding
+
+    k = 8
+    d = synth_batch(40, "alchemy", seed=9, k_dgl=k)
+    pe = lap_positional_encoding(d.edge_index.to(DEV), d.batch.to(DEV), k, d.num_graphs).cpu()
+    assert pe.shape == d.pos_enc.shape
+    off = checked = 0
+    for nb, ei in _per_graph(d):
+        w = torch.linalg.eigvalsh(sym_laplacian(ei, nb, torch.float64))
+        a, b = pe[off:off + nb], d.pos_enc[off:off + nb]
+        m = min(k, nb - 1)
+        assert a[:, m:].abs().max() == 0 if m < k else True
+        for j in range(m):
+            e = j + 1   # eigenvector index (the trivial one is dropped)
+            gap = min(float(w[e] - w[e - 1]), float(w[e + 1] - w[e]) if e + 1 < nb else 1.0)
+            if gap > 1e-2:
+                err = min(float((a[:, j] - b[:, j]).abs().max()), float((a[:, j] + b[:, j]).abs().max()))
+                assert err <= 1e-3, (j, err)
+                checked += 1
+        off += nb
+    assert checked > 20

@@ -30,7 +30,7 @@
 #define TC_MAXG 2
 static_assert(TC_MAXG == 2, "the tile -> group mapping below assumes at most two groups");
 #define TC_ESTAGE_BYTES (8 * 32 * 32 * 4)    // per-epilogue-warp [32 rows][32 cols] fp32 transposition tile
-#define TC_L2_AHEAD 3   // tiles requested into L2 ahead of the one-tile register prefetch
+#define TC_L2_AHEAD 2   // tiles requested into L2 ahead of the one-tile register prefetch
 
 struct TcArgs {
   const float* x;

@@ -238,10 +238,79 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
   if (lane == 0 && stat) { stat[row * 2] = mean; stat[row * 2 + 1] = rstd; }
 }
+// Vectorised variant (C % 4 == 0, C <= 128, 16-byte aligned rows): a warp takes four rows at a time, a lane owns one
+// float4 column group, all eight 128-bit loads are issued before the first reduction (the scalar kernel kept 32 B per
+// thread in flight and ran at 0.54 of the HBM peak).
+#define LN_ROWS 4
+__global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                const float* __restrict__ w,
+                                                                const float* __restrict__ beta, long long ld, long long R,
+                                                                int C, float eps, float* __restrict__ y,
+                                                                float* __restrict__ xsum, float* __restrict__ stat) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int col = lane * 4;
+  const bool in_ld = col < (int)ld, in_c = col < C;
+  float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), be4 = w4;
+  if (in_c) { w4 = ldg4(w + col); be4 = ldg4(beta + col); }
+  const float invC = 1.0f / (float)C;
+  for (long long r0 = warp0 * LN_ROWS; r0 < R; r0 += nwarps * LN_ROWS) {
+    float4 v[LN_ROWS];
+#pragma unroll
+    for (int k = 0; k < LN_ROWS; ++k) {
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (in_c && r0 + k < R) {
+        v[k] = ldg4(a + (r0 + k) * ld + col);
+        if (b) {
+          const float4 t = ldg4(b + (r0 + k) * ld + col);
+          v[k].x += t.x; v[k].y += t.y; v[k].z += t.z; v[k].w += t.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < LN_ROWS; ++k) {
+      if (r0 + k >= R) break;   // warp-uniform
+      const float mean = warp_sum((v[k].x + v[k].y) + (v[k].z + v[k].w)) * invC;
+      float q = 0.f;
+      if (in_c) {
+        const float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+        q = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+      }
+      const float var = warp_sum(q) * invC;
+      const float rstd = 1.0f / sqrtf(var + eps);
+      if (in_ld) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in_c) {
+          o.x = (v[k].x - mean) * rstd * w4.x + be4.x;
+          o.y = (v[k].y - mean) * rstd * w4.y + be4.y;
+          o.z = (v[k].z - mean) * rstd * w4.z + be4.z;
+          o.w = (v[k].w - mean) * rstd * w4.w + be4.w;
+        }
+        *reinterpret_cast<float4*>(y + (r0 + k) * ld + col) = o;
+        if (xsum) *reinterpret_cast<float4*>(xsum + (r0 + k) * ld + col) = v[k];
+      }
+      if (lane == 0 && stat) { stat[(r0 + k) * 2] = mean; stat[(r0 + k) * 2 + 1] = rstd; }
+    }
+  }
+}
+static bool ln_vec_ok(const void* p0, const void* p1, const void* p2, const void* p3, long long ld, int C) {
+  auto al = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
+  return C % 4 == 0 && C <= 128 && ld % 4 == 0 && ld <= 128 && al(p0) && al(p1) && al(p2) && al(p3);
+}
 extern "C" int sb_layernorm_fwd(const float* a, const float* b, const float* w, const float* beta, int64_t ld,
                                 int64_t R, int32_t C, float eps, float* y, float* xsum, float* stat, void* stream) {
   SB_CHECK_ARG(C >= 1 && C <= 256 && ld >= C && ld <= 256, "sb_layernorm_fwd: feature dim must be <= 256");
   if (R == 0) return SB_OK;
+  if (ln_vec_ok(a, b, y, xsum, ld, C) && ((uintptr_t)w & 15u) == 0 && ((uintptr_t)beta & 15u) == 0) {
+    long long blocks = sb_ceil_div(R, 8 * LN_ROWS);
+    const long long cap = (long long)sb_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    layernorm_fwd_vec_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, b, w, beta, ld, R, C, eps, y, xsum,
+                                                                                stat);
+    SB_CHECK_LAUNCH("sb_layernorm_fwd(vec)");
+    return SB_OK;
+  }
   layernorm_fwd_kernel<<<(unsigned)sb_ceil_div(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(a, b, w, beta, ld, R, C,
                                                                                            eps, y, xsum, stat);
   SB_CHECK_LAUNCH("sb_layernorm_fwd");
@@ -298,6 +367,77 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     atomicAdd(dwb + C + c, red[1][c]);
   }
 }
+__global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                                                const float* __restrict__ stat,
+                                                                const float* __restrict__ w, long long ld, long long R,
+                                                                int C, float* __restrict__ dx, double* __restrict__ dwb) {
+  __shared__ double red[2][128];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int col = lane * 4;
+  const bool in_ld = col < (int)ld, in_c = col < C;
+  float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (in_c) w4 = ldg4(w + col);
+  const float invC = 1.0f / (float)C;
+  double dw[4] = {0.0, 0.0, 0.0, 0.0}, db[4] = {0.0, 0.0, 0.0, 0.0};
+  const long long nwarps = (long long)gridDim.x * 8;
+  for (long long r0 = ((long long)blockIdx.x * 8 + wrp) * LN_ROWS; r0 < R; r0 += nwarps * LN_ROWS) {
+    float4 gv[LN_ROWS], xv[LN_ROWS];
+    float2 st[LN_ROWS];
+#pragma unroll
+    for (int k = 0; k < LN_ROWS; ++k) {
+      gv[k] = xv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      st[k] = make_float2(0.f, 0.f);
+      if (r0 + k < R) {
+        st[k] = __ldg(reinterpret_cast<const float2*>(stat + (r0 + k) * 2));
+        if (in_c) {
+          gv[k] = ldg4(g + (r0 + k) * ld + col);
+          xv[k] = ldg4(x + (r0 + k) * ld + col);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < LN_ROWS; ++k) {
+      if (r0 + k >= R) break;   // warp-uniform
+      const float mean = st[k].x, rstd = st[k].y;
+      const float gi[4] = {gv[k].x, gv[k].y, gv[k].z, gv[k].w};
+      const float xi[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
+      const float wi[4] = {w4.x, w4.y, w4.z, w4.w};
+      float gw[4], xh[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xh[j] = in_c ? (xi[j] - mean) * rstd : 0.f;
+        gw[j] = gi[j] * wi[j];
+        s1 += gw[j];
+        s2 = fmaf(gw[j], xh[j], s2);
+        dw[j] += (double)gi[j] * (double)xh[j];
+        db[j] += (double)gi[j];
+      }
+      s1 = warp_sum(s1) * invC;
+      s2 = warp_sum(s2) * invC;
+      if (in_ld) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in_c) {
+          o.x = rstd * (gw[0] - s1 - xh[0] * s2);
+          o.y = rstd * (gw[1] - s1 - xh[1] * s2);
+          o.z = rstd * (gw[2] - s1 - xh[2] * s2);
+          o.w = rstd * (gw[3] - s1 - xh[3] * s2);
+        }
+        *reinterpret_cast<float4*>(dx + (r0 + k) * ld + col) = o;
+      }
+    }
+  }
+  for (int c = threadIdx.x; c < 128; c += blockDim.x) { red[0][c] = 0.0; red[1][c] = 0.0; }
+  __syncthreads();
+  if (in_c) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { atomicAdd(&red[0][col + j], dw[j]); atomicAdd(&red[1][col + j], db[j]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(dwb + c, red[0][c]);
+    atomicAdd(dwb + C + c, red[1][c]);
+  }
+}
 extern "C" int sb_layernorm_bwd(const float* g, const float* x, const float* stat, const float* w, int64_t ld,
                                 int64_t R, int32_t C, float* dx, double* dwb, void* stream) {
   SB_CHECK_ARG(C >= 1 && C <= 256 && ld >= C && ld <= 256, "sb_layernorm_bwd: feature dim must be <= 256");
@@ -305,6 +445,11 @@ extern "C" int sb_layernorm_bwd(const float* g, const float* x, const float* sta
   long long blocks = sb_ceil_div(R, 8 * 4);
   const long long cap = (long long)sb_num_sms() * 4;
   if (blocks > cap) blocks = cap;
+  if (ln_vec_ok(g, x, dx, w, ld, C)) {
+    layernorm_bwd_vec_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, x, stat, w, ld, R, C, dx, dwb);
+    SB_CHECK_LAUNCH("sb_layernorm_bwd(vec)");
+    return SB_OK;
+  }
   layernorm_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, x, stat, w, ld, R, C, dx, dwb);
   SB_CHECK_LAUNCH("sb_layernorm_bwd");
   return SB_OK;

@@ -51,13 +51,14 @@ int sb_slot_layout(const int32_t* graph_ptr, int32_t B, int32_t k, int32_t maske
                    int64_t* row_ptr, int64_t* vec_ptr, int32_t* unit_ptr, int64_t* summary, void* stream);
 int sb_agg_units(const int32_t* graph_ptr, int32_t B, int32_t k, int32_t masked, int32_t tile_rows,
                  int32_t* unit_ptr, void* stream);
-/* unit_desc[U][12] int32: one record per aggregate work unit = (graph, slot chunk) tile of <= tile_rows rows:
- * {row_rel lo, hi, n_b, rows, node0, ceil(2^32/n_b), first edge / edge count of the graph in the CSR by destination,
- * the same for the CSR by source, 0, 0}.  cap_units = records allocated (U <= N if masked else B*k). */
 /* nbr_pack[N]: per node, up to four local neighbour ids (id - first node of its graph) of one CSR, a byte each in
  * CSR order, 0xFF = empty; 0xFE in byte 3 = degree > 4 or id > 253 (the aggregate walks the CSR for that node). */
 int sb_pack_neighbours(const int64_t* batch, const int32_t* graph_ptr, const int32_t* nbr_ptr, const int32_t* nbr_idx,
                        int64_t N, uint32_t* nbr_pack, void* stream);
+/* unit_desc[U][12] int32: one record per aggregate work unit = (graph, slot chunk) tile of <= tile_rows rows:
+ * {row_rel lo, hi, n_b, rows, node0, ceil(2^32/n_b), first edge / edge count of the graph in the CSR by destination,
+ * the same for the CSR by source, 0, 0}.  cap_units = records allocated (U <= N if masked else B*k).  The producer warp
+ * of the TMA aggregate finds its tile with one coalesced load of this record. */
 int sb_agg_unit_desc(const int32_t* graph_ptr, const int64_t* row_ptr, const int32_t* unit_ptr, const int32_t* in_ptr,
                      const int32_t* out_ptr, int32_t B, int32_t k, int32_t masked, int32_t tile_rows,
                      int32_t* unit_desc, int64_t cap_units, void* stream);

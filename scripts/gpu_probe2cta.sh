@@ -1,2 +1,2 @@
 #!/bin/bash
-timeout 60 ./scripts/build/tc_probe_2cta 2>&1 | tee gpurun_out/tc_probe_2cta.log; echo "rc=${PIPESTATUS[0]}"
+timeout 60 ./scripts/build/tc_probe_2cta_pipe 2>&1 | tee gpurun_out/tc_probe_2cta_pipe.log; echo "rc=${PIPESTATUS[0]}"

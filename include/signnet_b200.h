@@ -117,8 +117,14 @@ int sb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t w_rs, int
                   float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N, int32_t pro, const float* pa,
                   const float* pc, int32_t relu, double* stats, int32_t accumulate, void* stream);
 /* 1: contractions with 16 <= K,N <= 128 run on tcgen05 (3xTF32, linear_tc.cu); 0: fp32 FFMA everywhere.  Returns the
- * previous setting (-1 = not yet decided; env SB_DISABLE_TC=1 also selects FFMA). */
+ * previous setting (-1 = not yet decided; env SB_DISABLE_TC=1 also selects FFMA).  Values 2..4 select an EXPERIMENTAL
+ * kernel for the fast shapes of sb_linear_fwd (same contract and arithmetic; everything else stays on the default
+ * kernels): 2 = CTA pair (linear_tc_pair.cu, env SB_LINEAR_PAIR=1), 3 = TMA-fed operands and TMA stores
+ * (linear_tc_tma.cu, env SB_LINEAR_TMA=1), 4 = 3 with the raw tile as the head operand (env SB_LINEAR_TMA=2). */
 int sb_set_tensor_cores(int32_t enable);
+/* Which kernel the last block launch of sb_linear_fwd used: 0 FFMA, 1 tcgen05, 2..4 as above, -1 none yet (the
+ * rank-1 / row-dot streaming kernels do not update it).  Diagnostics for the tests and scripts/pair_check.cu. */
+int sb_last_linear_kernel(void);
 /* dw[n*rs + k*cs] (+)= sum gy[., n] * f(x[., k]);  db[n] (+)= sum gy[., n]   (deterministic two-stage reduction) */
 int sb_linear_wgrad(const float* gy, int64_t ldg, const float* x, int64_t ldx, int64_t R, int32_t G, int32_t N,
                     int32_t K, int32_t pro, const float* pa, const float* pc, float* dw, int64_t dw_rs,

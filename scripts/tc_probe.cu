@@ -48,9 +48,10 @@ __global__ void __launch_bounds__(256, 1) probe(const float* A, const float* B, 
     SPLIT(va.x, ah.x, al.x) SPLIT(va.y, ah.y, al.y) SPLIT(va.z, ah.z, al.z) SPLIT(va.w, ah.w, al.w)
     SPLIT(vb.x, bh.x, bl.x) SPLIT(vb.y, bh.y, bl.y) SPLIT(vb.z, bh.z, bl.z) SPLIT(vb.w, bh.w, bl.w)
     const uint32_t off = kb * TILE_BYTES + sw128_off(r, c);
-    *reinterpret_cast<float4*>(a_hi + off) = split ? ah : va;
+    // split 2: heads are the RAW fp32 words, tails = x - trunc_tf32(x): correct only if the tensor core truncates
+    *reinterpret_cast<float4*>(a_hi + off) = (split == 1) ? ah : va;
     *reinterpret_cast<float4*>(a_lo + off) = al;
-    *reinterpret_cast<float4*>(b_hi + off) = split ? bh : vb;
+    *reinterpret_cast<float4*>(b_hi + off) = (split == 1) ? bh : vb;
     *reinterpret_cast<float4*>(b_lo + off) = bl;
   }
   if (tid == 0) {
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256, 1) probe(const float* A, const float* B, 
 
 int main() {
   for (int K : {32, 128}) {
-    for (int split = 0; split < 2; ++split) {
+    for (int split = 0; split < 3; ++split) {
       std::vector<float> A(M * K), B(N * K), D(M * N, -1.f);
       srand(1);
       for (auto& x : A) x = (float)rand() / RAND_MAX * 2 - 1;

@@ -261,18 +261,38 @@ int sb_linear_tc_launch(const float* x, int64_t ldx, const float* w, int64_t w_r
                         float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N, int32_t pro,
                         const float* pa, const float* pc, int32_t relu, double* stats, int32_t accumulate,
                         int32_t ycols, cudaStream_t st);
+// CTA-pair variant (linear_tc_pair.cu), opt-in
+int sb_linear_tc_pair_launch(const float* x, int64_t ldx, const float* w, int64_t w_rs, int64_t w_cs,
+                             const float* bias, float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N,
+                             int32_t pro, const float* pa, const float* pc, int32_t relu, double* stats,
+                             int32_t accumulate, int32_t ycols, cudaStream_t st);
+// TMA-fed variant (linear_tc_tma.cu), opt-in
+int sb_linear_tc_tma_launch(const float* x, int64_t ldx, const float* w, int64_t w_rs, int64_t w_cs, const float* bias,
+                            float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N, int32_t pro,
+                            const float* pa, const float* pc, int32_t relu, double* stats, int32_t accumulate,
+                            int32_t ycols, int32_t rawhead, cudaStream_t st);
+// -1 undecided, 0 FFMA, 1 tcgen05 (default); experimental kernels for the fast shapes of sb_linear_fwd:
+// 2 CTA pair, 3 TMA-fed, 4 TMA-fed with the raw tile as the head operand
 static int g_use_tc = -1;
+static int g_last_variant = -1;
+extern "C" int sb_last_linear_kernel(void) { return g_last_variant; }
 extern "C" int sb_set_tensor_cores(int32_t enable) {
   const int old = g_use_tc;
-  g_use_tc = enable ? 1 : 0;
+  g_use_tc = (enable >= 2 && enable <= 4) ? enable : (enable ? 1 : 0);
   return old;
 }
 static bool use_tc() {
   if (g_use_tc < 0) {
     const char* e = getenv("SB_DISABLE_TC");
-    g_use_tc = (e && e[0] == '1') ? 0 : 1;
+    const char* p = getenv("SB_LINEAR_PAIR");
+    const char* t = getenv("SB_LINEAR_TMA");
+    g_use_tc = 1;
+    if (p && p[0] == '1') g_use_tc = 2;
+    if (t && t[0] == '1') g_use_tc = 3;
+    if (t && t[0] == '2') g_use_tc = 4;
+    if (e && e[0] == '1') g_use_tc = 0;
   }
-  return g_use_tc == 1;
+  return g_use_tc >= 1;
 }
 
 int sb_rank1_fwd_launch(const float* x, int64_t ldx, const float* w, int64_t w_rs, const float* bias, float* y,
@@ -348,9 +368,23 @@ extern "C" int sb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_
       const bool last_n = (n0 + 128 >= N);
       a.ycols = last_n ? (int)((ldy - n0 < 128) ? (ldy - n0) : 128) : 128;
       int rc = SB_ERR_UNSUPPORTED;
-      if (use_tc())
-        rc = sb_linear_tc_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro, a.pa,
-                                 a.pc, a.relu, a.stats, a.accumulate, a.ycols, st);
+      int variant = 0;
+      if (use_tc()) {
+        variant = g_use_tc;
+        if (g_use_tc == 2)
+          rc = sb_linear_tc_pair_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro,
+                                        a.pa, a.pc, a.relu, a.stats, a.accumulate, a.ycols, st);
+        if (g_use_tc >= 3)
+          rc = sb_linear_tc_tma_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro,
+                                       a.pa, a.pc, a.relu, a.stats, a.accumulate, a.ycols, g_use_tc == 4, st);
+        if (rc == SB_ERR_UNSUPPORTED) {
+          variant = 1;
+          rc = sb_linear_tc_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro, a.pa,
+                                   a.pc, a.relu, a.stats, a.accumulate, a.ycols, st);
+        }
+      }
+      if (rc == SB_ERR_UNSUPPORTED) variant = 0;
+      g_last_variant = variant;
       if (rc == SB_ERR_UNSUPPORTED)
         rc = (nn <= 64 && a.ycols <= 64) ? launch_linear<64>(a, st) : launch_linear<128>(a, st);
       if (rc != SB_OK) return rc;

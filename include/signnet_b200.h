@@ -120,7 +120,9 @@ int sb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t w_rs, int
  * previous setting (-1 = not yet decided; env SB_DISABLE_TC=1 also selects FFMA).  Values 2..4 select an EXPERIMENTAL
  * kernel for the fast shapes of sb_linear_fwd (same contract and arithmetic; everything else stays on the default
  * kernels): 2 = CTA pair (linear_tc_pair.cu, env SB_LINEAR_PAIR=1), 3 = TMA-fed operands and TMA stores
- * (linear_tc_tma.cu, env SB_LINEAR_TMA=1), 4 = 3 with the raw tile as the head operand (env SB_LINEAR_TMA=2). */
+ * (linear_tc_tma.cu, env SB_LINEAR_TMA=1), 4 = 3 with the raw tile as the head operand (env SB_LINEAR_TMA=2),
+ * 5 / 6 = split weight resident in tensor memory + 7-stage TMA ring (linear_tc_ws.cu, env SB_LINEAR_TMA=3 / 4;
+ * 6 = raw heads; compiled, not yet run on a GPU). */
 int sb_set_tensor_cores(int32_t enable);
 /* Which kernel the last block launch of sb_linear_fwd used: 0 FFMA, 1 tcgen05, 2..4 as above, -1 none yet (the
  * rank-1 / row-dot streaming kernels do not update it).  Diagnostics for the tests and scripts/pair_check.cu. */

@@ -1,5 +1,6 @@
 // Standalone check of the experimental Linear kernels THROUGH THE C ABI, no torch.  usage: pair_check [mode]
-//   mode 2 = CTA pair (csrc/linear_tc_pair.cu, default), 3 = TMA-fed, 4 = TMA-fed with raw heads (csrc/linear_tc_tma.cu).
+//   mode 2 = CTA pair (csrc/linear_tc_pair.cu, default), 3 = TMA-fed, 4 = TMA-fed with raw heads (csrc/linear_tc_tma.cu),
+//   5 / 6 = weight resident in tensor memory (csrc/linear_tc_ws.cu; 6 = raw heads).
 //   For a list of shapes run sb_linear_fwd with the validated single-CTA tcgen05 kernel (sb_set_tensor_cores(1)) and with
 //   the kernel under test (sb_set_tensor_cores(mode)) on the same device buffers and compare outputs and BatchNorm
 //   statistics (modes 2 and 3: same MMAs in the same order on the same split operands -> must be bit-identical; mode 4
@@ -40,7 +41,7 @@ static int run(const Case& c, int mode, const float* x, const float* w, const fl
 
 int main(int argc, char** argv) {
   const int mode_ut = (argc > 1) ? atoi(argv[1]) : 2;
-  const bool exact = mode_ut != 4;
+  const bool exact = mode_ut == 2 || mode_ut == 3;   // 4, 6: truncated heads; 5, 6: transposed MMA (order inside the tensor core unknown)
   printf("kernel under test: sb_set_tensor_cores(%d)\n", mode_ut);
   const Case cases[] = {
       {8200, 1, 32, 32, 0, 0, 1, 0, 0},       // 65 tiles: odd -> the peer's last tile is dead

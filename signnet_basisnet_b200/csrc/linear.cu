@@ -271,14 +271,19 @@ int sb_linear_tc_tma_launch(const float* x, int64_t ldx, const float* w, int64_t
                             float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N, int32_t pro,
                             const float* pa, const float* pc, int32_t relu, double* stats, int32_t accumulate,
                             int32_t ycols, int32_t rawhead, cudaStream_t st);
+// weight-stationary-in-tensor-memory variant (linear_tc_ws.cu), opt-in
+int sb_linear_tc_ws_launch(const float* x, int64_t ldx, const float* w, int64_t w_rs, int64_t w_cs, const float* bias,
+                           float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N, int32_t pro,
+                           const float* pa, const float* pc, int32_t relu, double* stats, int32_t accumulate,
+                           int32_t ycols, int32_t rawhead, cudaStream_t st);
 // -1 undecided, 0 FFMA, 1 tcgen05 (default); experimental kernels for the fast shapes of sb_linear_fwd:
-// 2 CTA pair, 3 TMA-fed, 4 TMA-fed with the raw tile as the head operand
+// 2 CTA pair, 3 TMA-fed, 4 TMA-fed with the raw tile as the head operand, 5 / 6 weight in tensor memory (6: raw heads)
 static int g_use_tc = -1;
 static int g_last_variant = -1;
 extern "C" int sb_last_linear_kernel(void) { return g_last_variant; }
 extern "C" int sb_set_tensor_cores(int32_t enable) {
   const int old = g_use_tc;
-  g_use_tc = (enable >= 2 && enable <= 4) ? enable : (enable ? 1 : 0);
+  g_use_tc = (enable >= 2 && enable <= 6) ? enable : (enable ? 1 : 0);
   return old;
 }
 static bool use_tc() {
@@ -290,6 +295,8 @@ static bool use_tc() {
     if (p && p[0] == '1') g_use_tc = 2;
     if (t && t[0] == '1') g_use_tc = 3;
     if (t && t[0] == '2') g_use_tc = 4;
+    if (t && t[0] == '3') g_use_tc = 5;
+    if (t && t[0] == '4') g_use_tc = 6;
     if (e && e[0] == '1') g_use_tc = 0;
   }
   return g_use_tc >= 1;
@@ -374,7 +381,10 @@ extern "C" int sb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_
         if (g_use_tc == 2)
           rc = sb_linear_tc_pair_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro,
                                         a.pa, a.pc, a.relu, a.stats, a.accumulate, a.ycols, st);
-        if (g_use_tc >= 3)
+        if (g_use_tc >= 5)
+          rc = sb_linear_tc_ws_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro,
+                                      a.pa, a.pc, a.relu, a.stats, a.accumulate, a.ycols, g_use_tc == 6, st);
+        else if (g_use_tc >= 3)
           rc = sb_linear_tc_tma_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro,
                                        a.pa, a.pc, a.relu, a.stats, a.accumulate, a.ycols, g_use_tc == 4, st);
         if (rc == SB_ERR_UNSUPPORTED) {

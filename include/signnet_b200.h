@@ -127,6 +127,9 @@ int sb_set_tensor_cores(int32_t enable);
 /* Which kernel the last block launch of sb_linear_fwd used: 0 FFMA, 1 tcgen05, 2..4 as above, -1 none yet (the
  * rank-1 / row-dot streaming kernels do not update it).  Diagnostics for the tests and scripts/pair_check.cu. */
 int sb_last_linear_kernel(void);
+/* Same for the last block launch of sb_linear_wgrad: 0 FFMA, 1 tcgen05 (wgrad_tc.cu), >= 3 the opt-in TMA-fed variant
+ * (wgrad_tc_tma.cu; selected by the same sb_set_tensor_cores values 3..6, N == K == 128 only). */
+int sb_last_wgrad_kernel(void);
 /* dw[n*rs + k*cs] (+)= sum gy[., n] * f(x[., k]);  db[n] (+)= sum gy[., n]   (deterministic two-stage reduction) */
 int sb_linear_wgrad(const float* gy, int64_t ldg, const float* x, int64_t ldx, int64_t R, int32_t G, int32_t N,
                     int32_t K, int32_t pro, const float* pa, const float* pc, float* dw, int64_t dw_rs,

@@ -145,6 +145,81 @@ int main(int argc, char** argv) {
       }
     }
   }
+  // ---- weight gradient: the TMA-fed variant (modes >= 3, N == K == 128) against the default tcgen05 wgrad kernel
+  if (mode_ut >= 3) {
+    const bool wexact = mode_ut == 3 || mode_ut == 5;   // rounded heads: same operands, same MMA order
+    float *ws, *dw1, *dw2, *db1, *db2;
+    CK(cudaMalloc(&ws, sb_linear_wgrad_workspace_floats() * 4));
+    CK(cudaMalloc(&dw1, 128 * 128 * 4)); CK(cudaMalloc(&dw2, 128 * 128 * 4)); CK(cudaMalloc(&db1, 512)); CK(cudaMalloc(&db2, 512));
+    struct WCase { long long R; int G, pro; };
+    const WCase wcases[] = {{20011, 2, 2}, {20011, 1, 0}, {575454, 2, 2}, {575454, 2, 0}};
+    for (const WCase& c : wcases) {
+      // g = y1 region (refilled), x = x
+      fill<<<1184, 256>>>(y1, (size_t)c.G * c.R * 128, 7u, 1.f, 0.f);
+      std::vector<float> h1(128 * 128), h2(128 * 128), b1(128), b2(128);
+      sb_set_tensor_cores(1);
+      int rc = sb_linear_wgrad(y1, 128, x, 128, c.R, c.G, 128, 128, c.pro, pa, pc, dw1, 128, 1, db1, 0, ws, nullptr);
+      if (rc || sb_last_wgrad_kernel() != 1) { printf("wgrad default: rc %d kernel %d %s\n", rc, sb_last_wgrad_kernel(), sb_last_error()); return 1; }
+      sb_set_tensor_cores(mode_ut);
+      rc = sb_linear_wgrad(y1, 128, x, 128, c.R, c.G, 128, 128, c.pro, pa, pc, dw2, 128, 1, db2, 0, ws, nullptr);
+      if (rc || sb_last_wgrad_kernel() != mode_ut) { printf("wgrad under test: rc %d kernel %d %s\n", rc, sb_last_wgrad_kernel(), sb_last_error()); return 1; }
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("wgrad kernel under test failed: %s\n", cudaGetErrorString(e)); return 1; }
+      CK(cudaMemcpy(h1.data(), dw1, 65536, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(h2.data(), dw2, 65536, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(b1.data(), db1, 512, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b2.data(), db2, 512, cudaMemcpyDeviceToHost));
+      size_t ndiff = 0; double maxd = 0, maxref = 0, maxdb = 0;
+      for (int i = 0; i < 128 * 128; ++i) {
+        if (memcmp(&h1[i], &h2[i], 4)) ++ndiff;
+        maxd = fmax(maxd, fabs((double)h1[i] - (double)h2[i]));
+        maxref = fmax(maxref, fabs((double)h1[i]));
+      }
+      for (int i = 0; i < 128; ++i) maxdb = fmax(maxdb, fabs((double)b1[i] - (double)b2[i]));
+      double maxerr = -1;
+      if (c.R < 100000) {   // fp64 host product at the small size
+        std::vector<float> hg((size_t)c.G * c.R * 128), hx((size_t)c.G * c.R * 128);
+        CK(cudaMemcpy(hg.data(), y1, hg.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hx.data(), x, hx.size() * 4, cudaMemcpyDeviceToHost));
+        std::vector<double> ref(128 * 128, 0.0);
+        std::vector<float> fx(128);
+        for (long long r = 0; r < c.G * c.R; ++r) {
+          const int g = (int)(r / c.R);
+          for (int k = 0; k < 128; ++k) {
+            float v = hx[r * 128 + k];
+            if (c.pro) { v = fmaf(hpa[g * 128 + k], v, hpc[g * 128 + k]); if (c.pro == 2) v = fmaxf(v, 0.f); }
+            fx[k] = v;
+          }
+          for (int n = 0; n < 128; ++n) {
+            const double gv = hg[r * 128 + n];
+            double* rr = &ref[n * 128];
+            for (int k = 0; k < 128; ++k) rr[k] += gv * (double)fx[k];
+          }
+        }
+        maxerr = 0;
+        for (int i = 0; i < 128 * 128; ++i) maxerr = fmax(maxerr, fabs(ref[i] - (double)h2[i]));
+      }
+      const bool ok = (wexact ? (ndiff == 0 && maxdb == 0) : (maxd <= 2e-5 * fmax(maxref, 1.0))) &&
+                      (maxerr < 0 || maxerr <= 2e-5 * fmax(maxref, 1.0));
+      if (!ok) ++bad;
+      printf("wgrad R=%lld G=%d pro=%d : %zu/16384 elements differ (max %.3e, max|dw| %.3f), max db diff %.3e, vs fp64 err %.3e  %s\n",
+             c.R, c.G, c.pro, ndiff, maxd, maxref, maxdb, maxerr, ok ? "OK" : "MISMATCH");
+      if (c.R >= 500000) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        for (int mi = 0; mi < 2; ++mi) {
+          sb_set_tensor_cores(mi ? mode_ut : 1);
+          for (int i = 0; i < 3; ++i) sb_linear_wgrad(y1, 128, x, 128, c.R, c.G, 128, 128, c.pro, pa, pc, dw2, 128, 1, db2, 0, ws, nullptr);
+          CK(cudaEventRecord(e0));
+          for (int i = 0; i < 10; ++i) sb_linear_wgrad(y1, 128, x, 128, c.R, c.G, 128, 128, c.pro, pa, pc, dw2, 128, 1, db2, 0, ws, nullptr);
+          CK(cudaEventRecord(e1));
+          CK(cudaDeviceSynchronize());
+          float ms = 0;
+          CK(cudaEventElapsedTime(&ms, e0, e1));
+          printf("   %s: %.1f us per call (wgrad + partial reduction), %.0f GB/s of g + x traffic\n", mi ? "under test" : "default   ",
+                 ms * 100.0, (double)c.G * c.R * 256 * 4 / (ms * 100.0 * 1e-6) / 1e9);
+        }
+      }
+    }
+  }
   printf(bad ? "pair_check: %d case(s) MISMATCH\n" : "pair_check: all cases OK\n", bad);
   return bad ? 1 : 0;
 }

@@ -78,6 +78,7 @@ def lib():
         L.sb_set_tensor_cores.restype = ctypes.c_int
         L.sb_set_tensor_cores.argtypes = [ctypes.c_int32]
         L.sb_last_linear_kernel.restype = ctypes.c_int
+        L.sb_last_wgrad_kernel.restype = ctypes.c_int
         L.sb_embedding_bwd_workspace_floats.restype = ctypes.c_int64
         L.sb_embedding_bwd_workspace_floats.argtypes = [ctypes.c_int32, ctypes.c_int32]
         for name, sig in _SIGNATURES.items():
@@ -91,7 +92,8 @@ def lib():
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["sb_last_error", "sb_abi_version", "sb_device_sm_count", "sb_gin_agg_tile_rows",
                                        "sb_linear_wgrad_workspace_floats", "sb_embedding_bwd_workspace_floats",
-                                       "sb_set_tensor_cores", "sb_last_linear_kernel"])
+                                       "sb_set_tensor_cores", "sb_last_linear_kernel",
+                                       "sb_last_wgrad_kernel"])
 
 
 def ptr(t):

@@ -279,8 +279,9 @@ int sb_linear_tc_ws_launch(const float* x, int64_t ldx, const float* w, int64_t 
 // -1 undecided, 0 FFMA, 1 tcgen05 (default); experimental kernels for the fast shapes of sb_linear_fwd:
 // 2 CTA pair, 3 TMA-fed, 4 TMA-fed with the raw tile as the head operand, 5 / 6 weight in tensor memory (6: raw heads)
 static int g_use_tc = -1;
-static int g_last_variant = -1;
+static int g_last_variant = -1, g_last_wgrad_variant = -1;
 extern "C" int sb_last_linear_kernel(void) { return g_last_variant; }
+extern "C" int sb_last_wgrad_kernel(void) { return g_last_wgrad_variant; }
 extern "C" int sb_set_tensor_cores(int32_t enable) {
   const int old = g_use_tc;
   g_use_tc = (enable >= 2 && enable <= 6) ? enable : (enable ? 1 : 0);
@@ -645,6 +646,11 @@ int sb_wgrad_tc_launch(const float* gy, int64_t ldg, const float* x, int64_t ldx
                        int32_t K, int32_t pro, const float* pa, const float* pc, float* dw, int64_t dw_rs,
                        int64_t dw_cs, float* db, int32_t accumulate, float* workspace, cudaStream_t st);
 
+int sb_wgrad_tc_tma_launch(const float* gy, int64_t ldg, const float* x, int64_t ldx, int64_t R, int32_t G, int32_t N,
+                           int32_t K, int32_t pro, const float* pa, const float* pc, float* dw, int64_t dw_rs,
+                           int64_t dw_cs, float* db, int32_t accumulate, float* workspace, int32_t rawhead,
+                           cudaStream_t st);
+
 template <int BN, int BK>
 static int launch_wgrad(WgArgs a, int N, int K, float* dw, long long rs, long long cs, float* db, int accumulate,
                         float* workspace, cudaStream_t st) {
@@ -703,9 +709,18 @@ extern "C" int sb_linear_wgrad(const float* gy, int64_t ldg, const float* x, int
       float* dwp = dw + (long long)n0 * dw_rs + (long long)k0 * dw_cs;
       float* dbp = (db && k0 == 0) ? db + n0 : nullptr;
       int rc = SB_ERR_UNSUPPORTED;
-      if (use_tc())
-        rc = sb_wgrad_tc_launch(a.g, a.ldg, a.x, a.ldx, a.R, a.G, a.N, a.K, a.pro, a.pa, a.pc, dwp, dw_rs, dw_cs, dbp,
-                                accumulate, workspace, st);
+      if (use_tc()) {
+        g_last_wgrad_variant = g_use_tc;
+        if (g_use_tc >= 3)   // opt-in TMA-fed variant (N == K == 128 only); raw heads in the modes that use them
+          rc = sb_wgrad_tc_tma_launch(a.g, a.ldg, a.x, a.ldx, a.R, a.G, a.N, a.K, a.pro, a.pa, a.pc, dwp, dw_rs, dw_cs,
+                                      dbp, accumulate, workspace, g_use_tc == 4 || g_use_tc == 6, st);
+        if (rc == SB_ERR_UNSUPPORTED) {
+          g_last_wgrad_variant = 1;
+          rc = sb_wgrad_tc_launch(a.g, a.ldg, a.x, a.ldx, a.R, a.G, a.N, a.K, a.pro, a.pa, a.pc, dwp, dw_rs, dw_cs, dbp,
+                                  accumulate, workspace, st);
+        }
+      }
+      if (rc == SB_ERR_UNSUPPORTED) g_last_wgrad_variant = 0;
       if (rc != SB_ERR_UNSUPPORTED) {
         if (rc != SB_OK) return rc;
         continue;

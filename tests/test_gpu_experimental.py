@@ -64,3 +64,42 @@ def test_experimental_linear_matches_default(mode, K, N, pro, relu, bias, transp
     assert_close_rel(stats[mode][:, 1].cpu(), (ref ** 2).sum(1).cpu(), 1e-5, what="col sumsq")
     if mode in (2, 3):  # same operands, same MMA order as the default kernel
         assert torch.equal(out[mode], out[1])
+
+
+@pytest.mark.parametrize("mode", [3, 4])
+@pytest.mark.parametrize("pro,bias", [(0, False), (2, True)])
+def test_experimental_wgrad_matches_default(mode, pro, bias):
+    """TMA-fed weight gradient (csrc/wgrad_tc_tma.cu, N == K == 128) against the default tcgen05 wgrad and fp64."""
+    from signnet_basisnet_b200 import _lib
+    from signnet_basisnet_b200.functional import linear_wgrad
+
+    torch.manual_seed(pro * 7 + mode)
+    G, R, N, K = 2, 4133, 128, 128
+    gy = torch.randn(G, R, N, device=DEV)
+    x = torch.randn(G, R, K, device=DEV)
+    pa, pc = (torch.rand(G, K) + 0.5).to(DEV), (torch.randn(G, K) * 0.3).to(DEV)
+    xin = x.double()
+    if pro:
+        xin = (xin * pa.double()[:, None, :] + pc.double()[:, None, :]).relu()
+    ref_w = torch.einsum("grn,grk->nk", gy.double(), xin)
+    ref_b = gy.double().sum((0, 1))
+
+    L = _lib.lib()
+    out = {}
+    try:
+        for m in (1, mode):
+            L.sb_set_tensor_cores(m)
+            dW = torch.full((N, K), float("nan"), device=DEV)
+            db = torch.full((N,), float("nan"), device=DEV) if bias else None
+            linear_wgrad(gy, N, x, K, R, G, N, K, dW, K, 1, db, pro=pro, pa=pa if pro else None, pc=pc if pro else None)
+            torch.cuda.synchronize()
+            assert L.sb_last_wgrad_kernel() == m, f"dispatcher fell back to kernel {L.sb_last_wgrad_kernel()}"
+            out[m] = (dW, db)
+    finally:
+        L.sb_set_tensor_cores(1)
+    assert_close_rel(out[mode][0].cpu(), ref_w.float().cpu(), 1e-5, what=f"wgrad mode {mode}")
+    if bias:
+        assert_close_rel(out[mode][1].cpu(), ref_b.float().cpu(), 1e-5, floor=float(gy.abs().sum((0, 1)).max()),
+                         what="dbias")
+    if mode == 3:  # rounded heads: same operands, same MMA order as the default kernel
+        assert torch.equal(out[mode][0], out[1][0])

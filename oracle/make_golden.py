@@ -114,6 +114,29 @@ def make_gin_net():
                 "grads": _grads(net)}, os.path.join(OUT, "dgl_gin_net.pt"))
 
 
+def make_gatedgcn_net():
+    """the reference's own GatedGCNNet (+ its masked_gin sign_inv_net; the structure of
+    configs/gatedgcn/GatedGCN_ZINC_LapPE_signinv_GIN_mask.json at a small width) on a small seeded batch."""
+    gg = ref_loader.gatedgcn_net()
+    import dgl
+    params = dict(num_atom_type=28, num_bond_type=4, hidden_dim=20, out_dim=20, in_feat_dropout=0.0, dropout=0.0, L=3,
+                  readout="mean", batch_norm=True, residual=True, edge_feat=True, device="cpu", pe_init="lap_pe",
+                  lap_method="sign_inv", lap_lspe=False, use_lapeig_loss=False, lambda_loss=1.0, alpha_loss=1e-4,
+                  pos_enc_dim=6, sign_inv_net="masked_gin", phi_out_dim=8, sign_inv_layers=3, sign_inv_activation="relu",
+                  pe_aggregate="concat")
+    torch.manual_seed(17)
+    net = gg.GatedGCNNet(params)
+    d = synth_batch(6, "zinc", seed=23, k_dgl=params["pos_enc_dim"])
+    g = dgl.BatchedGraph(d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph)
+    sd0 = _sd(net)
+    pe = net.sign_inv_net(g, d.pos_enc.unsqueeze(-1)).squeeze(-1)
+    out, _ = net(g, d.x[:, 0], pe, d.edge_attr.reshape(-1), None)
+    w = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
+    (out * w).sum().backward()
+    torch.save({"params": params, "state_dict": sd0, "data": _data_dict(d), "w": w, "out": out.detach(),
+                "grads": _grads(net), "state_dict_after": _sd(net)}, os.path.join(OUT, "dgl_gatedgcn_net.pt"))
+
+
 def make_eq_deepsets():
     """Row a14: the reference's own SignPlus(EqDeepSetsEncoder) (phi on [k, n, 1] and rho on [n, 2k], training.py:207-218)."""
     models = ref_loader.learningfilters_models()
@@ -148,6 +171,7 @@ if __name__ == "__main__":
     make_alchemy()
     make_dgl()
     make_gin_net()
+    make_gatedgcn_net()
     make_eq_deepsets()
     make_ign()
     for f in sorted(os.listdir(OUT)):

@@ -79,6 +79,21 @@ def gin_net():
     return importlib.import_module("nets.ZINC_graph_regression.gin_net")
 
 
+def gatedgcn_net():
+    """-> nets.ZINC_graph_regression.gatedgcn_net of /root/reference/GraphPrediction (the GatedGCN predictor the
+    `GatedGCN_ZINC_LapPE_signinv_GIN_mask.json` configuration — cfg 4's k = 37 — selects)."""
+    _ensure(_SHIM)
+    _ensure(os.path.join(REF_ROOT, "GraphPrediction"))
+    return importlib.import_module("nets.ZINC_graph_regression.gatedgcn_net")
+
+
+def zinc_train_loop():
+    """-> train.train_ZINC_graph_regression of /root/reference/GraphPrediction (`handle_lap`: the PE baselines)."""
+    _ensure(_SHIM)
+    _ensure(os.path.join(REF_ROOT, "GraphPrediction"))
+    return importlib.import_module("train.train_ZINC_graph_regression")
+
+
 def learningfilters_models():
     """-> LearningFilters/models.py (EqDeepSetsEncoder, row a14), imported unmodified; needs the PyG stand-ins because
     the file also defines spectral-GNN baselines that are off the hot path."""

@@ -338,6 +338,81 @@ def gin_net(h_idx, pos_enc, src, dst, num_nodes_per_graph, sd, n_layers, readout
     return F.linear(y, sd[f"{p}MLP_layer.FC_layers.{L}.weight"], sd[f"{p}MLP_layer.FC_layers.{L}.bias"])
 
 
+def gated_gcn_layer(h, e, src, dst, sd, p, batch_norm=True, residual=True, training=True):
+    """GatedGCNLayer.forward with graph_norm=False, dropout 0 (GraphPrediction/layers/gatedgcn_layer.py:36-77):
+    e' = D h_src + E h_dst + C e;  sigma = sigmoid(e');  h' = A h + (sum_in B h_src * sigma) / (sum_in sigma + 1e-6);
+    BatchNorm1d on both, ReLU, residual (dropped when the layer changes the width, :24-25)."""
+    lin = lambda x, n: F.linear(x, sd[f"{p}{n}.weight"], sd[f"{p}{n}.bias"])
+    Ah, Bh, Dh, Eh, Ce = lin(h, "A"), lin(h, "B"), lin(h, "D"), lin(h, "E"), lin(e, "C")
+    e_new = (Dh.index_select(0, src) + Eh.index_select(0, dst)) + Ce
+    sigma = torch.sigmoid(e_new)
+    N = h.shape[0]
+    ssh = torch.zeros(N, Bh.shape[1], dtype=h.dtype).index_add(0, dst, Bh.index_select(0, src) * sigma)
+    ss = torch.zeros(N, Bh.shape[1], dtype=h.dtype).index_add(0, dst, sigma)
+    h_new = Ah + ssh / (ss + 1e-6)
+    if batch_norm:
+        h_new = _bn(h_new, sd, f"{p}bn_node_h.", training)
+        e_new = _bn(e_new, sd, f"{p}bn_node_e.", training)
+    h_new, e_new = _relu(h_new), _relu(e_new)
+    if residual and h.shape[1] == h_new.shape[1]:
+        h_new, e_new = h + h_new, e + e_new
+    return h_new, e_new
+
+
+def gatedgcn_net(h_idx, pos_enc, e_idx, src, dst, num_nodes_per_graph, sd, n_layers, readout="mean", edge_feat=True,
+                 pe_aggregate="add", batch_norm=True, residual=True, training=True, p=""):
+    """GatedGCNNet.forward, `pe_init='lap_pe'`, no LSPE (GraphPrediction/nets/ZINC_graph_regression/gatedgcn_net.py:86-135):
+    h = embedding_h(atom) (+ | concat-project) embedding_p(pos_enc); e = embedding_e(bond) (or Linear(1) of ones);
+    L x GatedGCNLayer; mean/sum readout; MLPReadout (layers/mlp_readout_layer.py:9-25)."""
+    h = sd[p + "embedding_h.weight"][h_idx]
+    pp = F.linear(pos_enc, sd[p + "embedding_p.weight"], sd[p + "embedding_p.bias"])
+    if pe_aggregate == "concat":
+        h = F.linear(torch.cat([h, pp], dim=1), sd[p + "pe_proj.weight"], sd[p + "pe_proj.bias"])
+    else:
+        h = h + pp
+    if edge_feat:
+        e = sd[p + "embedding_e.weight"][e_idx]
+    else:
+        e = F.linear(torch.ones(src.numel(), 1, dtype=h.dtype), sd[p + "embedding_e.weight"], sd[p + "embedding_e.bias"])
+    for l in range(n_layers):
+        h, e = gated_gcn_layer(h, e, src, dst, sd, f"{p}layers.{l}.", batch_norm, residual, training)
+    n = torch.as_tensor(num_nodes_per_graph)
+    seg = torch.repeat_interleave(torch.arange(n.numel()), n)
+    hg = torch.zeros(n.numel(), h.shape[1], dtype=h.dtype).index_add_(0, seg, h)
+    if readout != "sum":
+        hg = hg / n.to(h.dtype).clamp(min=1).unsqueeze(1)
+    y, L = hg, 2
+    for l in range(L):
+        y = _relu(F.linear(y, sd[f"{p}MLP_layer.FC_layers.{l}.weight"], sd[f"{p}MLP_layer.FC_layers.{l}.bias"]))
+    return F.linear(y, sd[f"{p}MLP_layer.FC_layers.{L}.weight"], sd[f"{p}MLP_layer.FC_layers.{L}.bias"])
+
+
+def handle_lap(pos_enc, num_nodes_per_graph, lap_method, sign_flip=None):
+    """The positional-encoding baselines of train/train_ZINC_graph_regression.py:12-47 other than `sign_inv`:
+    'sign_flip' (random column signs; the caller passes the draw), 'abs_val', 'canonical' (per graph and column:
+    flip when the column has fewer non-negative than negative entries OR less non-negative than negative mass;
+    `less_nonneg + less_norm` is a boolean OR in torch), 'none'."""
+    if lap_method == "sign_flip":
+        return pos_enc * sign_flip.unsqueeze(0)
+    if lap_method == "abs_val":
+        return pos_enc.abs()
+    if lap_method == "none":
+        return pos_enc
+    if lap_method != "canonical":
+        raise ValueError("invalid laplacian method")
+    n = torch.as_tensor(num_nodes_per_graph)
+    seg = torch.repeat_interleave(torch.arange(n.numel()), n)
+    seg_sum = lambda x: torch.zeros(n.numel(), x.shape[1], dtype=x.dtype).index_add_(0, seg, x)
+    less_nonneg = seg_sum((pos_enc >= 0).float()) < seg_sum((pos_enc < 0).float())
+    nonneg, neg = pos_enc.clone(), pos_enc.clone()
+    nonneg[pos_enc < 0] = 0
+    neg[pos_enc >= 0] = 0
+    less_norm = seg_sum(nonneg) < seg_sum(neg.abs())
+    flip = -(less_nonneg + less_norm).float()
+    flip[flip == 0] = 1
+    return flip.index_select(0, seg) * pos_enc
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # LearningFilters flavour (rows a14, a15): single-graph SignNet (DeepSets phi) and BasisNet IGN 2->1
 # --------------------------------------------------------------------------------------------------------------------

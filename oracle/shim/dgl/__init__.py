@@ -1,8 +1,10 @@
 """TEST INFRASTRUCTURE ONLY — minimal stand-in for DGL (unpinned by the reference; APIs imply 0.5–0.6.x) so that
-GraphPrediction/layers/{deepsigns,gnns,mlp}.py import unmodified.  Published semantics restated:
+GraphPrediction/layers/{deepsigns,gnns,mlp,gatedgcn_layer}.py and nets/ZINC_graph_regression/{gin,gatedgcn}_net.py import
+unmodified.  Published semantics restated:
 dgl.nn.pytorch.GINConv(apply_func, 'sum', init_eps=0, learn_eps=False):
     rst = (1 + eps) * feat + sum_{u->v} feat_u ;  return apply_func(rst) ; eps is a buffer unless learn_eps."""
 import torch
+from . import function  # noqa: F401
 from . import nn  # noqa: F401
 
 
@@ -22,6 +24,24 @@ class BatchedGraph:
 
     def num_nodes(self):
         return int(self._bnn.sum())
+
+    # message passing with the dgl.function builtins (gatedgcn_layer.py:48-53)
+    def apply_edges(self, func):
+        kind, u, v, out = func
+        assert kind == "u_add_v"
+        self.edata[out] = self.ndata[u].index_select(0, self.src) + self.ndata[v].index_select(0, self.dst)
+
+    def update_all(self, message_func, reduce_func):
+        kind, a, b, m_name = message_func
+        if kind == "u_mul_e":
+            m = self.ndata[a].index_select(0, self.src) * self.edata[b]
+        elif kind == "copy_e":
+            m = self.edata[a]
+        else:
+            raise NotImplementedError(kind)
+        rkind, r_in, r_out = reduce_func
+        assert rkind == "sum" and r_in == m_name
+        self.ndata[r_out] = torch.zeros(self.num_nodes(), *m.shape[1:], dtype=m.dtype).index_add(0, self.dst, m)
 
 
 def _segments(g):
@@ -46,3 +66,8 @@ def max_nodes(g, key):
     seg, n = _segments(g)
     x = g.ndata[key]
     return torch.stack([x[seg == b].max(0).values for b in range(n.numel())])
+
+
+def broadcast_nodes(g, x):
+    """dgl.broadcast_nodes: repeat a per-graph row for every node of that graph (train_ZINC_graph_regression.py:41)."""
+    return x.repeat_interleave(g.batch_num_nodes(), 0)

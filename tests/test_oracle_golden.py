@@ -105,3 +105,22 @@ def test_eq_deepsets_golden(golden_dir, name):
     assert_close_rel(out, m["out"], 1e-5, what=f"SignPlus(EqDeepSets) {name}")
     (out * m["w"]).sum().backward()
     assert_grads_close({k: v.grad for k, v in sd.items()}, {k[len("model."):]: v for k, v in m["grads"].items()}, 2e-5, name)
+
+
+def test_gatedgcn_net_golden(golden_dir):
+    """oracle restatement of the DGL GatedGCNNet predictor (+ its masked_gin sign_inv_net, the structure
+    of GatedGCN_ZINC_LapPE_signinv_GIN_mask.json) vs the reference's own output, gradients and running statistics."""
+    g = _load(golden_dir, "dgl_gatedgcn_net.pt")
+    d, prm = Data(**g["data"]), g["params"]
+    sd = _leaf(g["state_dict"])
+    sub = {k[len("sign_inv_net."):]: v for k, v in sd.items() if k.startswith("sign_inv_net.")}
+    pe = restate.masked_gin_deepsigns(d.pos_enc.unsqueeze(-1), d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph, sub,
+                                      prm["sign_inv_layers"], prm["pos_enc_dim"]).squeeze(-1)
+    out = restate.gatedgcn_net(d.x[:, 0], pe, d.edge_attr.reshape(-1), d.edge_index[0], d.edge_index[1],
+                               d.num_nodes_per_graph, sd, prm["L"], prm["readout"], prm["edge_feat"], prm["pe_aggregate"])
+    assert_close_rel(out, g["out"], 2e-5, what="GatedGCNNet")
+    (out * g["w"]).sum().backward()
+    assert_grads_close({k: v.grad for k, v in sd.items() if not k.endswith(".eps")}, g["grads"], 5e-5, "GatedGCNNet")
+    for k, v in g["state_dict_after"].items():
+        if "running_" in k and k.startswith("layers."):
+            torch.testing.assert_close(sd[k], v, rtol=1e-5, atol=1e-6)

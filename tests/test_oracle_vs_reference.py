@@ -169,3 +169,67 @@ def test_eq_deepsets_sign_plus(shape, cin, hid, cout, L):
     got = {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
     assert set(want) == set(got)
     assert_grads_close(got, want, 2e-5, "eq_deepsets")
+
+
+GATEDGCN_NET_PARAMS = dict(num_atom_type=28, num_bond_type=4, hidden_dim=20, out_dim=20, in_feat_dropout=0.0, dropout=0.0,
+                           L=3, readout="mean", batch_norm=True, residual=True, edge_feat=True, device="cpu",
+                           pe_init="lap_pe", lap_method="sign_inv", lap_lspe=False, use_lapeig_loss=False,
+                           lambda_loss=1.0, alpha_loss=1e-4, pos_enc_dim=6, sign_inv_net="masked_gin", phi_out_dim=8,
+                           sign_inv_layers=3, sign_inv_activation="relu", pe_aggregate="concat")
+
+
+@pytest.mark.parametrize("pe_aggregate,edge_feat,readout", [("concat", True, "mean"), ("add", True, "sum"),
+                                                             ("add", False, "mean")])
+def test_gatedgcn_net_predictor(pe_aggregate, edge_feat, readout):
+    """the GatedGCN predictor of GatedGCN_ZINC_LapPE_signinv_GIN_mask.json (gatedgcn_net.py:86-135,
+    gatedgcn_layer.py:36-77) consuming the sign-invariant PE."""
+    gg = ref_loader.gatedgcn_net()   # puts the stand-in dgl on sys.path
+    import dgl
+
+    torch.manual_seed(9)
+    params = dict(GATEDGCN_NET_PARAMS, pe_aggregate=pe_aggregate, edge_feat=edge_feat, readout=readout)
+    net = gg.GatedGCNNet(params)
+    k = params["pos_enc_dim"]
+    d = synth_batch(6, "zinc", seed=21, k_dgl=k)
+    g = dgl.BatchedGraph(d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph)
+    sd = _leafify(_clone_sd(net))
+    atoms, bonds = d.x[:, 0], d.edge_attr.reshape(-1)
+    pe = net.sign_inv_net(g, d.pos_enc.unsqueeze(-1)).squeeze(-1)
+    ref, _ = net(g, atoms, pe, bonds, None)
+    pe_o = restate.masked_gin_deepsigns(d.pos_enc.unsqueeze(-1), d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph,
+                                        {k2[len("sign_inv_net."):]: v for k2, v in sd.items() if k2.startswith("sign_inv_net.")},
+                                        params["sign_inv_layers"], k).squeeze(-1)
+    out = restate.gatedgcn_net(atoms, pe_o, bonds, d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph, sd,
+                               params["L"], readout, edge_feat, pe_aggregate)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-5)
+    w = torch.randn_like(ref)
+    (ref * w).sum().backward()
+    (out * w).sum().backward()
+    want = {k2: v.grad for k2, v in net.named_parameters() if v.grad is not None}
+    got = {k2: v.grad for k2, v in sd.items() if v.requires_grad and v.grad is not None and not k2.endswith(".eps")}
+    assert set(want) == set(got)   # dgl GINConv eps (inside sign_inv_net) is a buffer
+    assert_grads_close(got, want, 5e-5, "gatedgcn_net")
+    for name, buf in net.named_buffers():   # BatchNorm running statistics of both streams
+        if buf.is_floating_point():
+            torch.testing.assert_close(sd[name], buf, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("method", ["sign_flip", "abs_val", "canonical", "none"])
+def test_handle_lap_baselines(method):
+    """The non-learned PE baselines of train_ZINC_graph_regression.py:12-47 (bit-exact: sign / abs only)."""
+    import types
+
+    tr = ref_loader.zinc_train_loop()   # puts the stand-in dgl on sys.path
+    import dgl
+
+    d = synth_batch(7, "zinc", seed=4, k_dgl=8)
+    g = dgl.BatchedGraph(d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph)
+    model = types.SimpleNamespace(lap_method=method)
+    torch.manual_seed(3)
+    ref = tr.handle_lap(model, d.pos_enc.clone(), g, "cpu")
+    torch.manual_seed(3)
+    flip = torch.rand(d.pos_enc.size(1))
+    flip[flip >= 0.5] = 1.0
+    flip[flip < 0.5] = -1.0
+    out = restate.handle_lap(d.pos_enc.clone(), d.num_nodes_per_graph, method, sign_flip=flip)
+    assert torch.equal(out, ref)

@@ -178,6 +178,22 @@ int sb_gine_agg_fwd(const float* x, const float* e, const float* eps, const int3
 int sb_gine_agg_bwd(const float* dA, const float* x, const float* e, const float* eps, const int64_t* edge_index,
                     const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_eid, int64_t N, int64_t E,
                     int32_t ld, float* dx, float* de, double* deps, void* stream);
+/* ---- K10: edge-gated aggregate of the GatedGCN predictor (GraphPrediction/layers/gatedgcn_layer.py:48-54: dgl
+ * apply_edges(u_add_v) + update_all(u_mul_e, sum) + update_all(copy_e, sum)) on [N, ld] node rows / [E, ld] edge rows:
+ * e_out_k = (Dh[src_k] + Eh[dst_k]) + Ce_k;  h_out_i = Ah_i + sum_in(Bh[src] * sigmoid(e_out)) / (sum_in sigmoid(e_out)
+ * + 1e-6); ss_out / ssh_out [N, ld] keep the two sums for the backward.  Backward: given dh [N, ld] and de [E, ld] (may
+ * be NULL) writes dBh, dDh, dEh [N, ld] and dCe [E, ld] (= d e_out); dAh = dh.  Deterministic (CSR / CSC order). */
+int sb_gated_agg_fwd(const float* Ah, const float* Bh, const float* Dh, const float* Eh, const float* Ce,
+                     const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid, int64_t N, int32_t ld,
+                     float* e_out, float* h_out, float* ss_out, float* ssh_out, void* stream);
+int sb_gated_agg_bwd(const float* dh, const float* de, const float* Bh, const float* e_new, const float* ss,
+                     const float* ssh, const int64_t* edge_index, const int32_t* in_ptr, const int32_t* in_eid,
+                     const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_eid, int64_t N, int64_t E,
+                     int32_t ld, float* dBh, float* dDh, float* dEh, float* dCe, void* stream);
+/* K11: the `canonical` sign convention of train/train_ZINC_graph_regression.py:26-42 (PE baseline): per graph and
+ * column flip the sign when the column has fewer non-negative than negative entries or less non-negative mass. */
+int sb_canonical_sign(const float* pe, int64_t ldp, const int32_t* graph_ptr, int64_t B, int32_t k, float* out,
+                      int64_t ldo, void* stream);
 /* graph read-out: scatter(x, batch, reduce='add'|'mean') (model.py:58-61) on the sorted batch */
 int sb_segment_pool_fwd(const float* x, int64_t ldx, const int32_t* graph_ptr, int32_t B, int32_t C, int32_t mean,
                         float* out, int64_t ldo, void* stream);

@@ -37,6 +37,9 @@ _SIGNATURES = {
     "sb_affine2": "ppppppp" + "ll" + "ii" + "p",
     "sb_gine_agg_fwd": "pppppp" + "li" + "p" + "p",
     "sb_gine_agg_bwd": "pppp" + "pppp" + "lli" + "ppp" + "p",
+    "sb_gated_agg_fwd": "ppppp" + "ppp" + "li" + "pppp" + "p",
+    "sb_gated_agg_bwd": "pppppp" + "p" + "ppppp" + "lli" + "pppp" + "p",
+    "sb_canonical_sign": "plp" + "li" + "pl" + "p",
     "sb_segment_pool_fwd": "plp" + "iii" + "pl" + "p",
     "sb_segment_pool_bwd": "plpp" + "lii" + "pl" + "p",
     "sb_embedding_fwd": "plp" + "iil" + "pl" + "ip" + "p",

@@ -1,0 +1,198 @@
+// K10 — the edge-gated aggregate of the GatedGCN predictor (GraphPrediction/layers/gatedgcn_layer.py:48-54, dgl builtins
+// u_add_v / u_mul_e / copy_e + sum) on [N, ld] node rows and [E, ld] edge rows (edge-id order):
+//     e'_k   = (Dh[src_k] + Eh[dst_k]) + Ce_k                      sigma_k = sigmoid(e'_k)
+//     h'_i   = Ah_i + (sum_{k: dst_k = i} Bh[src_k] * sigma_k) / (sum_{k: dst_k = i} sigma_k + 1e-6)
+// and K11 — the `canonical` sign convention of train/train_ZINC_graph_regression.py:26-42 (a PE baseline).
+// One warp per destination node (forward) / per edge and per node (backward), float4 lanes over the feature dim,
+// incoming edges visited in stable CSR (= edge-id) order: sums are deterministic and in the order of the CPU
+// reference's index_add_; no atomics anywhere.  HBM/L2-bound integer+float streaming work: the node tensors
+// (N <= ~25k rows x 512 B) stay in L2, the edge tensors are read / written once.
+// STATUS: written after the round's GPU budget was spent: compiles for sm_100a, covered by tests/test_gpu_gatedgcn.py
+// (golden fixture of the reference's own GatedGCNNet), not yet run on a GPU.
+#include "common.cuh"
+#include "../../include/signnet_b200.h"
+
+__device__ __forceinline__ float gt_sigmoid(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+__global__ void __launch_bounds__(256) gated_agg_fwd_kernel(const float* __restrict__ Ah, const float* __restrict__ Bh,
+                                                            const float* __restrict__ Dh, const float* __restrict__ Eh,
+                                                            const float* __restrict__ Ce,
+                                                            const int32_t* __restrict__ in_ptr,
+                                                            const int32_t* __restrict__ in_src,
+                                                            const int32_t* __restrict__ in_eid, long long N, int ld,
+                                                            float* __restrict__ e_out, float* __restrict__ h_out,
+                                                            float* __restrict__ ss_out, float* __restrict__ ssh_out) {
+  const long long node = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (node >= N) return;
+  const int beg = __ldg(in_ptr + node), end = __ldg(in_ptr + node + 1);
+  for (int c4 = lane; c4 < (ld >> 2); c4 += 32) {
+    const long long col = c4 * 4;
+    const float4 eh = ldg4(Eh + node * ld + col);
+    float ssh[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int p = beg; p < end; ++p) {
+      const long long j = __ldg(in_src + p), k = __ldg(in_eid + p);
+      const float4 dh = ldg4(Dh + j * ld + col), ce = ldg4(Ce + k * ld + col), bh = ldg4(Bh + j * ld + col);
+      const float d4[4] = {dh.x, dh.y, dh.z, dh.w}, e4[4] = {eh.x, eh.y, eh.z, eh.w}, c4v[4] = {ce.x, ce.y, ce.z, ce.w},
+                  b4[4] = {bh.x, bh.y, bh.z, bh.w};
+      float ev[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        ev[t] = __fadd_rn(__fadd_rn(d4[t], e4[t]), c4v[t]);
+        const float sg = gt_sigmoid(ev[t]);
+        ssh[t] = __fadd_rn(ssh[t], __fmul_rn(b4[t], sg));
+        ss[t] = __fadd_rn(ss[t], sg);
+      }
+      stg4_stream(e_out + k * ld + col, make_float4(ev[0], ev[1], ev[2], ev[3]));
+    }
+    const float4 ah = ldg4(Ah + node * ld + col);
+    float4 o;
+    o.x = __fadd_rn(ah.x, __fdiv_rn(ssh[0], __fadd_rn(ss[0], 1e-6f)));
+    o.y = __fadd_rn(ah.y, __fdiv_rn(ssh[1], __fadd_rn(ss[1], 1e-6f)));
+    o.z = __fadd_rn(ah.z, __fdiv_rn(ssh[2], __fadd_rn(ss[2], 1e-6f)));
+    o.w = __fadd_rn(ah.w, __fdiv_rn(ssh[3], __fadd_rn(ss[3], 1e-6f)));
+    *reinterpret_cast<float4*>(h_out + node * ld + col) = o;
+    *reinterpret_cast<float4*>(ss_out + node * ld + col) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+    *reinterpret_cast<float4*>(ssh_out + node * ld + col) = make_float4(ssh[0], ssh[1], ssh[2], ssh[3]);
+  }
+}
+
+extern "C" int sb_gated_agg_fwd(const float* Ah, const float* Bh, const float* Dh, const float* Eh, const float* Ce,
+                                const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid, int64_t N,
+                                int32_t ld, float* e_out, float* h_out, float* ss_out, float* ssh_out, void* stream) {
+  SB_CHECK_ARG(ld % 4 == 0 && ld > 0, "sb_gated_agg_fwd: ld must be a positive multiple of 4");
+  if (N == 0) return SB_OK;
+  gated_agg_fwd_kernel<<<(unsigned)sb_ceil_div(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      Ah, Bh, Dh, Eh, Ce, in_ptr, in_src, in_eid, N, ld, e_out, h_out, ss_out, ssh_out);
+  SB_CHECK_LAUNCH("sb_gated_agg_fwd");
+  return SB_OK;
+}
+
+// backward, edge part (one warp per edge k: j -> i):
+//   dssh_i = dh_i / (ss_i + 1e-6);  dss_i = -dh_i * ssh_i / (ss_i + 1e-6)^2
+//   dsigma_k = dssh_i * Bh_j + dss_i;   dCe_k = de_k + dsigma_k * sigma_k (1 - sigma_k)       (= d e'_k)
+__global__ void __launch_bounds__(256) gated_agg_bwd_edge_kernel(const float* __restrict__ dh, const float* __restrict__ de,
+                                                                 const float* __restrict__ Bh,
+                                                                 const float* __restrict__ e_new,
+                                                                 const float* __restrict__ ss,
+                                                                 const float* __restrict__ ssh,
+                                                                 const int64_t* __restrict__ src,
+                                                                 const int64_t* __restrict__ dst, long long E, int ld,
+                                                                 float* __restrict__ dCe) {
+  const long long k = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= E) return;
+  const long long j = src[k], i = dst[k];
+  for (int c4 = lane; c4 < (ld >> 2); c4 += 32) {
+    const long long col = c4 * 4;
+    const float4 g = ldg4(dh + i * ld + col), s = ldg4(ss + i * ld + col), sh = ldg4(ssh + i * ld + col);
+    const float4 b = ldg4(Bh + j * ld + col), ev = ldg4(e_new + k * ld + col);
+    float4 up = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (de) up = ldg4(de + k * ld + col);
+    const float g4[4] = {g.x, g.y, g.z, g.w}, s4[4] = {s.x, s.y, s.z, s.w}, sh4[4] = {sh.x, sh.y, sh.z, sh.w},
+                b4[4] = {b.x, b.y, b.z, b.w}, e4[4] = {ev.x, ev.y, ev.z, ev.w}, u4[4] = {up.x, up.y, up.z, up.w};
+    float o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float r = 1.0f / (s4[t] + 1e-6f);
+      const float dssh = g4[t] * r, dss = -g4[t] * sh4[t] * r * r;
+      const float sg = gt_sigmoid(e4[t]);
+      o[t] = u4[t] + (dssh * b4[t] + dss) * sg * (1.0f - sg);
+    }
+    *reinterpret_cast<float4*>(dCe + k * ld + col) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+// backward, node part (one warp per node v), fixed CSR / CSC order:
+//   dEh_v = sum_{k: dst_k = v} dCe_k;   dDh_v = sum_{k: src_k = v} dCe_k;   dBh_v = sum_{k: src_k = v} dssh_{dst_k} sigma_k
+__global__ void __launch_bounds__(256) gated_agg_bwd_node_kernel(
+    const float* __restrict__ dh, const float* __restrict__ e_new, const float* __restrict__ ss,
+    const float* __restrict__ dCe, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_eid,
+    const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_dst, const int32_t* __restrict__ out_eid,
+    long long N, int ld, float* __restrict__ dBh, float* __restrict__ dDh, float* __restrict__ dEh) {
+  const long long node = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (node >= N) return;
+  const int ib = __ldg(in_ptr + node), ie = __ldg(in_ptr + node + 1);
+  const int ob = __ldg(out_ptr + node), oe = __ldg(out_ptr + node + 1);
+  for (int c4 = lane; c4 < (ld >> 2); c4 += 32) {
+    const long long col = c4 * 4;
+    float4 aE = make_float4(0.f, 0.f, 0.f, 0.f), aD = aE, aB = aE;
+    for (int p = ib; p < ie; ++p) {
+      const float4 v = ldg4(dCe + (long long)__ldg(in_eid + p) * ld + col);
+      aE.x += v.x; aE.y += v.y; aE.z += v.z; aE.w += v.w;
+    }
+    for (int p = ob; p < oe; ++p) {
+      const long long k = __ldg(out_eid + p), t = __ldg(out_dst + p);
+      const float4 v = ldg4(dCe + k * ld + col), g = ldg4(dh + t * ld + col), s = ldg4(ss + t * ld + col),
+                   ev = ldg4(e_new + k * ld + col);
+      aD.x += v.x; aD.y += v.y; aD.z += v.z; aD.w += v.w;
+      aB.x += g.x / (s.x + 1e-6f) * gt_sigmoid(ev.x);
+      aB.y += g.y / (s.y + 1e-6f) * gt_sigmoid(ev.y);
+      aB.z += g.z / (s.z + 1e-6f) * gt_sigmoid(ev.z);
+      aB.w += g.w / (s.w + 1e-6f) * gt_sigmoid(ev.w);
+    }
+    *reinterpret_cast<float4*>(dEh + node * ld + col) = aE;
+    *reinterpret_cast<float4*>(dDh + node * ld + col) = aD;
+    *reinterpret_cast<float4*>(dBh + node * ld + col) = aB;
+  }
+}
+
+extern "C" int sb_gated_agg_bwd(const float* dh, const float* de, const float* Bh, const float* e_new, const float* ss,
+                                const float* ssh, const int64_t* edge_index, const int32_t* in_ptr,
+                                const int32_t* in_eid, const int32_t* out_ptr, const int32_t* out_dst,
+                                const int32_t* out_eid, int64_t N, int64_t E, int32_t ld, float* dBh, float* dDh,
+                                float* dEh, float* dCe, void* stream) {
+  SB_CHECK_ARG(ld % 4 == 0 && ld > 0, "sb_gated_agg_bwd: ld must be a positive multiple of 4");
+  SB_CHECK_ARG(dh && Bh && e_new && ss && ssh && dBh && dDh && dEh && dCe, "sb_gated_agg_bwd: null operand");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (E > 0) {
+    gated_agg_bwd_edge_kernel<<<(unsigned)sb_ceil_div(E * 32, 256), 256, 0, st>>>(dh, de, Bh, e_new, ss, ssh, edge_index,
+                                                                                edge_index + E, E, ld, dCe);
+    SB_CHECK_LAUNCH("sb_gated_agg_bwd(edge)");
+  }
+  if (N > 0) {
+    gated_agg_bwd_node_kernel<<<(unsigned)sb_ceil_div(N * 32, 256), 256, 0, st>>>(dh, e_new, ss, dCe, in_ptr, in_eid,
+                                                                                out_ptr, out_dst, out_eid, N, ld, dBh,
+                                                                                dDh, dEh);
+    SB_CHECK_LAUNCH("sb_gated_agg_bwd(node)");
+  }
+  return SB_OK;
+}
+
+// K11: out[i, c] = s(b, c) * pe[i, c] for node i of graph b, with s = -1 when column c of graph b has fewer non-negative
+// than negative entries OR less non-negative than negative mass, else +1 (train_ZINC_graph_regression.py:26-42:
+// `less_nonneg + less_norm` on bool tensors is a logical OR).  One warp per (graph, column); the per-graph sums run in
+// node order like dgl.sum_nodes on the CPU.  Counts are exact; the mass comparison is fp32 in node order.
+__global__ void __launch_bounds__(256) canonical_sign_kernel(const float* __restrict__ pe, long long ldp,
+                                                             const int32_t* __restrict__ gp, long long B, int k,
+                                                             float* __restrict__ out, long long ldo) {
+  const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= B * k) return;
+  const long long b = w / k;
+  const int c = (int)(w - b * k);
+  const int beg = gp[b], end = gp[b + 1];
+  float flip = 1.f;
+  if (lane == 0) {   // graphs have <= a few dozen nodes: a serial pass keeps the CPU summation order
+    int npos = 0, nneg = 0;
+    float spos = 0.f, sneg = 0.f;
+    for (int i = beg; i < end; ++i) {
+      const float v = pe[(long long)i * ldp + c];
+      if (v >= 0.f) { ++npos; spos = __fadd_rn(spos, v); }
+      else          { ++nneg; sneg = __fadd_rn(sneg, fabsf(v)); }
+    }
+    if (npos < nneg || spos < sneg) flip = -1.f;
+  }
+  flip = __shfl_sync(0xffffffffu, flip, 0);
+  for (int i = beg + lane; i < end; i += 32) out[(long long)i * ldo + c] = flip * pe[(long long)i * ldp + c];
+}
+
+extern "C" int sb_canonical_sign(const float* pe, int64_t ldp, const int32_t* graph_ptr, int64_t B, int32_t k, float* out,
+                                 int64_t ldo, void* stream) {
+  SB_CHECK_ARG(k >= 1 && ldp >= k && ldo >= k, "sb_canonical_sign: bad sizes");
+  if (B == 0) return SB_OK;
+  canonical_sign_kernel<<<(unsigned)sb_ceil_div(B * k * 32, 256), 256, 0, (cudaStream_t)stream>>>(pe, ldp, graph_ptr, B, k,
+                                                                                             out, ldo);
+  SB_CHECK_LAUNCH("sb_canonical_sign");
+  return SB_OK;
+}

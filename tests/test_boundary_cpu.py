@@ -95,7 +95,8 @@ def test_alchemy_config_parameter_count():
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
-@pytest.mark.parametrize("which", ["gin_deepsigns", "masked_gin_deepsigns", "gin_net", "ign2to1", "ign_basis_inv", "eq_deepsets"])
+@pytest.mark.parametrize("which", ["gin_deepsigns", "masked_gin_deepsigns", "gin_net", "gatedgcn_net", "gatedgcn_net_add",
+                                   "ign2to1", "ign_basis_inv", "eq_deepsets"])
 def test_state_dict_matches_reference_other_trees(which):
     """DGL and LearningFilters trees (rows a9-a11, a13-a15): same parameter / buffer names and shapes as the reference's
     own classes, so reference checkpoints load unchanged."""
@@ -116,6 +117,14 @@ def test_state_dict_matches_reference_other_trees(which):
                    lap_method="sign_inv", lap_lspe=False, use_lapeig_loss=False, lambda_loss=0.0, alpha_loss=0.0,
                    pos_enc_dim=5, sign_inv_net="gin", phi_out_dim=4, sign_inv_layers=3, sign_inv_activation="relu")
         ref, mine = ref_loader.gin_net().GINNet(prm), GINNet(prm)
+    elif which in ("gatedgcn_net", "gatedgcn_net_add"):
+        from signnet_basisnet_b200.gatedgcn_net import GatedGCNNet
+        prm = dict(num_atom_type=28, num_bond_type=4, hidden_dim=16, out_dim=16, in_feat_dropout=0.0, dropout=0.0, L=3,
+                   readout="mean", batch_norm=True, residual=True, edge_feat=which == "gatedgcn_net", device="cpu",
+                   pe_init="lap_pe", lap_method="sign_inv", lap_lspe=False, use_lapeig_loss=False, lambda_loss=1.0,
+                   alpha_loss=1e-4, pos_enc_dim=5, sign_inv_net="masked_gin", phi_out_dim=4, sign_inv_layers=3,
+                   sign_inv_activation="relu", pe_aggregate="concat" if which == "gatedgcn_net" else "add")
+        ref, mine = ref_loader.gatedgcn_net().GatedGCNNet(prm), GatedGCNNet(prm)
     elif which == "ign2to1":
         from signnet_basisnet_b200.basisnet import IGN2to1
         ign, _ = ref_loader.learningfilters()

@@ -137,6 +137,50 @@ def make_gatedgcn_net():
                 "grads": _grads(net), "state_dict_after": _sd(net)}, os.path.join(OUT, "dgl_gatedgcn_net.pt"))
 
 
+def _slim(sd, rows=32):
+    """DiscreteEncoder tables have 500 rows per feature (core/model_utils/elements.py:22) of which the ZINC-shape inputs
+    touch < 32: keep the fixture small by storing only the first `rows` rows (the tests zero-pad them back)."""
+    return {k: (v[:rows].clone() if ".embeddings." in k and v.dim() == 2 and v.shape[0] > rows else v) for k, v in sd.items()}
+
+
+def make_zinc_pyg():
+    """The GINESignNetPyG tree (cfg 3; the model bench.py times).  `out` and `state_dict_after` come from the unmodified
+    reference (core/sign_net.py SignNetGNN, training-mode forward under no_grad: its backward cannot run under torch 2.11
+    because of in-place writes on ReLU outputs); `grads` are torch autograd through oracle/restate.sign_net_gnn, whose
+    forward is checked here to reproduce the reference's output (asserted below)."""
+    import restate
+    sn = ref_loader.gine_signnet_pyg()
+    torch.manual_seed(19)
+    cfg = dict(n_hid=24, n_out=1, nl_signnet=3, nl_gnn=2)
+    d = synth_batch(7, "zinc", seed=29)
+    model = sn.SignNetGNN(None, None, **cfg).train()
+    for lyr in model.sign_net.rho.transformer_layers:
+        lyr.slf_attn.attention.dropout.p = 0.0
+    with torch.no_grad():   # non-trivial BatchNorm affines / eps so that every parameter matters
+        for n_, p in model.named_parameters():
+            if n_.endswith("bn.weight"):
+                p.uniform_(0.5, 1.5)
+            elif n_.endswith("bn.bias") or n_.endswith("eps"):
+                p.uniform_(-0.3, 0.3)
+    sd0 = _sd(model)
+    with torch.no_grad():
+        out = model(copy.copy(d))
+    sd = {k: v.clone() for k, v in sd0.items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    out_o = restate.sign_net_gnn(d, sd, cfg["nl_signnet"], cfg["nl_gnn"], nl_rho=1, ignore_eigval=True)
+    torch.testing.assert_close(out_o, out, rtol=1e-5, atol=1e-5)
+    w = torch.randn(out.shape, generator=torch.Generator().manual_seed(4))
+    (out_o * w).sum().backward()
+    grads = {k: v.grad.detach().clone() for k, v in sd.items() if v.requires_grad and v.grad is not None}
+    after = {k: v for k, v in _sd(model).items() if "running_" in k or "num_batches" in k}
+    torch.save({"cfg": cfg, "state_dict": _slim(sd0), "data": _data_dict(d), "w": w, "out": out.detach(),
+                "grads": _slim(grads), "embedding_rows_kept": 32,
+                "grads_source": "torch autograd through oracle/restate.py (reference backward not runnable)",
+                "buffers_after": after}, os.path.join(OUT, "zinc_pyg.pt"))
+
+
 def make_eq_deepsets():
     """Row a14: the reference's own SignPlus(EqDeepSetsEncoder) (phi on [k, n, 1] and rho on [n, 2k], training.py:207-218)."""
     models = ref_loader.learningfilters_models()
@@ -172,6 +216,7 @@ if __name__ == "__main__":
     make_dgl()
     make_gin_net()
     make_gatedgcn_net()
+    make_zinc_pyg()
     make_eq_deepsets()
     make_ign()
     for f in sorted(os.listdir(OUT)):

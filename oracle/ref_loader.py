@@ -58,6 +58,16 @@ def alchemy():
     return sn
 
 
+def gine_signnet_pyg():
+    """-> core.sign_net of /root/reference/GINESignNetPyG (the PyG ZINC tree: cfg 3 and the model bench.py times).
+    Imported unmodified; FORWARD only - its in-place `x += previous_x` / `q += residual` on ReLU outputs
+    (core/sign_net.py:46, core/model.py:67, core/model_utils/transformer_module.py:100,125) make torch 2.11 autograd
+    reject the backward, so gradients of this tree are pinned through the oracle's own autograd of the same forward."""
+    _ensure(_SHIM)
+    _ensure(os.path.join(REF_ROOT, "GINESignNetPyG"))
+    return importlib.import_module("core.sign_net")
+
+
 def alchemy_transform():
     _ensure(_SHIM)
     _ensure(os.path.join(REF_ROOT, "Alchemy"))

@@ -15,6 +15,9 @@
  *     ld = feature dim rounded up to 4 floats, padding columns kept at 0).  Only valid slots exist, so the reference's
  *     boolean-mask bookkeeping (sign_net.py:38-39, masked_layers.py:59-60) has no counterpart.
  *   - `G` ("groups") = leading dimension over which BatchNorm statistics are kept separate (the two sign passes).
+ *   - process-wide state: one process drives one GPU.  The only mutable globals are the kernel-selection switch
+ *     (sb_set_tensor_cores) with its two diagnostics (sb_last_linear_kernel / sb_last_wgrad_kernel) and the one-time
+ *     per-kernel cudaFuncSetAttribute; set the switch before launching work from several host threads.
  */
 #ifndef SIGNNET_B200_H
 #define SIGNNET_B200_H

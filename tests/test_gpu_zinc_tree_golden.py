@@ -25,6 +25,8 @@ def _fatten(sd, rows_full=500):
     return out
 
 
+@pytest.mark.xfail(strict=False, reason="written after round 1's last GPU visit: outcome on a GPU not yet observed "
+                                        "(XPASS = parity holds; remove this marker once seen)")
 def test_signnetgnn_zinc_tree_golden(golden_dir):
     from signnet_basisnet_b200.sign_net import SignNetGNN
 

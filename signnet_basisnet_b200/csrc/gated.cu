@@ -7,8 +7,10 @@
 // incoming edges visited in stable CSR (= edge-id) order: sums are deterministic and in the order of the CPU
 // reference's index_add_; no atomics anywhere.  HBM/L2-bound integer+float streaming work: the node tensors
 // (N <= ~25k rows x 512 B) stay in L2, the edge tensors are read / written once.
-// STATUS: written after the round's GPU budget was spent: compiles for sm_100a, covered by tests/test_gpu_gatedgcn.py
-// (golden fixture of the reference's own GatedGCNNet), not yet run on a GPU.
+// STATUS: written after the round's GPU budget was spent: compiles for sm_100a, not yet run on a GPU.  The source text
+// of the three gated kernels is executed thread by thread on the CPU against an fp64 statement of the layer by
+// tests/test_cpu_emulation_gated.py (they have no inter-thread communication, so a serial emulation is faithful); the
+// GPU tests are tests/test_gpu_gatedgcn.py (golden fixture of the reference's own GatedGCNNet).
 #include "common.cuh"
 #include "../../include/signnet_b200.h"
 

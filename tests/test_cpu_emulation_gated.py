@@ -35,6 +35,14 @@ static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 static inline void stg4_stream(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// broadcast from lane 0 only (the one pattern canonical_sign_kernel uses): lanes run in order 0..31, so lane 0 has
+// already deposited its value when the other lanes of the warp ask for it
+static float shfl_lane0_;
+static inline float __shfl_sync(unsigned, float v, int src_lane) {
+  if (src_lane != 0) __builtin_trap();
+  if ((threadIdx.x & 31) == 0) shfl_lane0_ = v;
+  return shfl_lane0_;
+}
 #define LAUNCH(kernel, grid, ...)                                                       \
   for (unsigned b_ = 0; b_ < (unsigned)(grid); ++b_)                                    \
     for (unsigned t_ = 0; t_ < 256; ++t_) {                                             \
@@ -55,6 +63,10 @@ extern "C" void emu_bwd(const float* dh, const float* de, const float* Bh, const
   LAUNCH(gated_agg_bwd_edge_kernel, (E * 32 + 255) / 256, dh, de, Bh, e_new, ss, ssh, ei, ei + E, E, ld, dCe)
   LAUNCH(gated_agg_bwd_node_kernel, (N * 32 + 255) / 256, dh, e_new, ss, dCe, in_ptr, in_eid, out_ptr, out_dst, out_eid, N,
          ld, dBh, dDh, dEh)
+}
+extern "C" void emu_canonical(const float* pe, long long ldp, const int32_t* gp, long long B, int k, float* out,
+                              long long ldo) {
+  LAUNCH(canonical_sign_kernel, (B * k * 32 + 255) / 256, pe, ldp, gp, B, k, out, ldo)
 }
 """
 
@@ -79,8 +91,8 @@ def emu(tmp_path_factory):
         pytest.skip("g++ not available")
     src = open(os.path.join(ROOT, "signnet_basisnet_b200", "csrc", "gated.cu")).read()
     parts = _functions(src, r"__device__ __forceinline__ float gt_sigmoid") + _functions(
-        src, r"__global__ void __launch_bounds__\(256\) gated_agg_\w+")
-    assert len(parts) == 4
+        src, r"__global__ void __launch_bounds__\(256\) (?:gated_agg|canonical_sign)_\w+")
+    assert len(parts) == 5
     d = tmp_path_factory.mktemp("emu")
     cpp, so = os.path.join(d, "emu.cpp"), os.path.join(d, "libemu.so")
     open(cpp, "w").write(PRELUDE + "\n".join(parts) + WRAPPERS)
@@ -143,3 +155,22 @@ def test_gated_aggregate_source_emulated(emu, B, C, ld, with_de):
         assert not torch.isnan(got).any(), name
         torch.testing.assert_close(got[:, :C].double(), want, rtol=2e-5, atol=2e-5, msg=name)
         assert float(got[:, C:].abs().sum()) == 0, name
+
+
+def test_canonical_sign_source_emulated(emu):
+    """canonical_sign_kernel (one warp per (graph, column), lane-0 decision broadcast) against oracle/restate.handle_lap,
+    which is bit-exact against train_ZINC_graph_regression.py:26-42."""
+    import restate
+
+    d = synth_batch(13, "zinc", seed=8, k_dgl=8)
+    pe = d.pos_enc.contiguous()
+    n = torch.as_tensor(d.num_nodes_per_graph)
+    gp = torch.zeros(n.numel() + 1, dtype=torch.int32)
+    gp[1:] = torch.cumsum(n, 0).to(torch.int32)
+    out = torch.full_like(pe, float("nan"))
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    emu.emu_canonical(P(pe), ctypes.c_longlong(pe.stride(0)), P(gp), ctypes.c_longlong(n.numel()), ctypes.c_int(pe.shape[1]),
+                      P(out), ctypes.c_longlong(out.stride(0)))
+    ref = restate.handle_lap(pe.clone(), d.num_nodes_per_graph, "canonical")
+    assert torch.equal(out, ref)
+    assert bool((ref != pe).any())   # the case really flips some columns

@@ -149,3 +149,22 @@ def test_state_dict_matches_reference_other_trees(which):
     for k in a:
         assert a[k].shape == b[k].shape, k
     mine.load_state_dict(b)
+
+
+def test_kernel_selection_switch_roundtrip():
+    """sb_set_tensor_cores is host-only state: every documented mode is accepted and reported back; anything else
+    collapses to on (1) / off (0).  (No compute call: runs without a GPU.)"""
+    L = _lib.lib()
+    first = L.sb_set_tensor_cores(1)
+    assert first in (-1, 0, 1, 2, 3, 4, 5, 6)
+    try:
+        for mode in (0, 1, 2, 3, 4, 5, 6):
+            L.sb_set_tensor_cores(mode)
+            assert L.sb_set_tensor_cores(mode) == mode
+        L.sb_set_tensor_cores(7)
+        assert L.sb_set_tensor_cores(1) == 1
+        L.sb_set_tensor_cores(-3)
+        assert L.sb_set_tensor_cores(1) == 1
+        assert L.sb_last_linear_kernel() in (-1, 0, 1, 2, 3, 4, 5, 6) and L.sb_last_wgrad_kernel() in (-1, 0, 1, 3, 4, 5, 6)
+    finally:
+        L.sb_set_tensor_cores(1 if first < 0 else first)

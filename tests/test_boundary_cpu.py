@@ -168,3 +168,22 @@ def test_kernel_selection_switch_roundtrip():
         assert L.sb_last_linear_kernel() in (-1, 0, 1, 2, 3, 4, 5, 6) and L.sb_last_wgrad_kernel() in (-1, 0, 1, 3, 4, 5, 6)
     finally:
         L.sb_set_tensor_cores(1 if first < 0 else first)
+
+
+def test_gnn_model_loader_mirrors_load_net():
+    """load_net.gnn_model (nets/ZINC_graph_regression/load_net.py:26-36): same names, same classes; unbuilt predictors raise."""
+    from signnet_basisnet_b200.gatedgcn_net import GatedGCNNet
+    from signnet_basisnet_b200.gin_net import GINNet
+    from signnet_basisnet_b200.load_net import gnn_model
+
+    prm = dict(num_atom_type=28, num_bond_type=4, hidden_dim=16, out_dim=16, in_feat_dropout=0.0, dropout=0.0, L=2,
+               readout="mean", batch_norm=True, residual=True, edge_feat=True, device="cpu", pe_init="lap_pe",
+               lap_method="sign_inv", lap_lspe=False, use_lapeig_loss=False, lambda_loss=1.0, alpha_loss=1e-4,
+               pos_enc_dim=5, sign_inv_net="masked_gin", phi_out_dim=4, sign_inv_layers=2, sign_inv_activation="relu",
+               pe_aggregate="add")
+    assert isinstance(gnn_model("GIN", prm), GINNet) and isinstance(gnn_model("GatedGCN", prm), GatedGCNNet)
+    for name in ("GAT", "PNA", "Transformer"):
+        with pytest.raises(NotImplementedError):
+            gnn_model(name, prm)
+    with pytest.raises(KeyError):
+        gnn_model("nope", prm)

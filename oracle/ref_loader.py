@@ -97,6 +97,13 @@ def gatedgcn_net():
     return importlib.import_module("nets.ZINC_graph_regression.gatedgcn_net")
 
 
+def pna_net():
+    """-> nets.ZINC_graph_regression.pna_net of /root/reference/GraphPrediction (PNA predictor, section 8f rank 4)."""
+    _ensure(_SHIM)
+    _ensure(os.path.join(REF_ROOT, "GraphPrediction"))
+    return importlib.import_module("nets.ZINC_graph_regression.pna_net")
+
+
 def zinc_train_loop():
     """-> train.train_ZINC_graph_regression of /root/reference/GraphPrediction (`handle_lap`: the PE baselines)."""
     _ensure(_SHIM)

@@ -387,6 +387,82 @@ def gatedgcn_net(h_idx, pos_enc, e_idx, src, dst, num_nodes_per_graph, sd, n_lay
     return F.linear(y, sd[f"{p}MLP_layer.FC_layers.{L}.weight"], sd[f"{p}MLP_layer.FC_layers.{L}.bias"])
 
 
+def pna_aggregate(msg, dst, N, avg_d_log, aggregators=("mean", "max", "min", "std"),
+                  scalers=("identity", "amplification", "attenuation")):
+    """PNATower.reduce_func_for_h (GraphPrediction/layers/pna_layer.py:50-55, pna_utils.py:12-31,73-84): per destination
+    node, over its D incoming messages: cat over aggregators [mean | max | min | sqrt(relu(E[x^2] - E[x]^2) + 1e-5)],
+    then cat over scalers [identity | * log(D+1)/avg_d | * avg_d/log(D+1)].  Nodes without incoming edges keep zeros
+    (DGL does not call the reduce function for them)."""
+    C = msg.shape[1]
+    deg = torch.bincount(dst, minlength=N)
+    D = deg.clamp(min=1).to(msg.dtype).unsqueeze(1)
+    idx = dst.unsqueeze(1).expand(-1, C)
+    s1 = torch.zeros(N, C, dtype=msg.dtype).index_add(0, dst, msg)
+    s2 = torch.zeros(N, C, dtype=msg.dtype).index_add(0, dst, msg * msg)
+    mean = s1 / D
+    outs = {"mean": mean,
+            "max": torch.full((N, C), float("-inf"), dtype=msg.dtype).scatter_reduce(0, idx, msg, "amax", include_self=True),
+            "min": torch.full((N, C), float("inf"), dtype=msg.dtype).scatter_reduce(0, idx, msg, "amin", include_self=True),
+            "std": torch.sqrt(torch.relu(s2 / D - mean * mean) + 1e-5), "sum": s1}
+    h = torch.cat([outs[a] for a in aggregators], dim=1)
+    logd = torch.log(deg.clamp(min=1).to(msg.dtype) + 1).unsqueeze(1)
+    scale = {"identity": torch.ones_like(logd), "amplification": logd / avg_d_log, "attenuation": avg_d_log / logd}
+    h = torch.cat([h * scale[sc] for sc in scalers], dim=1)
+    return torch.where((deg > 0).unsqueeze(1), h, torch.zeros_like(h))
+
+
+def pna_layer(h, e, src, dst, snorm_n, sd, p, towers, divide_input, avg_d_log, graph_norm=True, batch_norm=True,
+              residual=True, edge_features=True, training=True, aggregators=("mean", "max", "min", "std"),
+              scalers=("identity", "amplification", "attenuation")):
+    """PNALayer.forward with pretrans_layers = posttrans_layers = 1, dropout 0 (pna_layer.py:16-82,134-153): per tower
+    Linear(cat[h_src, h_dst, e]) -> aggregate -> Linear(cat[h, agg]) -> * snorm_n -> BatchNorm; towers concatenated ->
+    Linear + LeakyReLU(0.01) mixing network -> residual (dropped when the layer changes the width)."""
+    N, in_dim = h.shape
+    tin = in_dim // towers if divide_input else in_dim
+    outs = []
+    for t in range(towers):
+        ht = h[:, t * tin:(t + 1) * tin] if divide_input else h
+        q = f"{p}towers.{t}."
+        z = [ht.index_select(0, src), ht.index_select(0, dst)] + ([e] if edge_features else [])
+        msg = F.linear(torch.cat(z, dim=1), sd[q + "pretrans_h.fully_connected.0.linear.weight"],
+                       sd[q + "pretrans_h.fully_connected.0.linear.bias"])
+        agg = pna_aggregate(msg, dst, N, avg_d_log, aggregators, scalers)
+        ho = F.linear(torch.cat([ht, agg], dim=1), sd[q + "posttrans_h.fully_connected.0.linear.weight"],
+                      sd[q + "posttrans_h.fully_connected.0.linear.bias"])
+        if graph_norm:
+            ho = ho * snorm_n
+        if batch_norm:
+            ho = _bn(ho, sd, q + "batchnorm_h.", training)
+        outs.append(ho)
+    hc = torch.cat(outs, dim=1)
+    ho = F.leaky_relu(F.linear(hc, sd[p + "mixing_network_h.linear.weight"], sd[p + "mixing_network_h.linear.bias"]), 0.01)
+    if residual and ho.shape[1] == in_dim:
+        ho = h + ho
+    return ho
+
+
+def pna_net(h_idx, pos_enc, e_idx, src, dst, num_nodes_per_graph, snorm_n, sd, n_layers, towers, avg_d_log,
+            readout="sum", divide_input_first=True, divide_input_last=True, graph_norm=True, batch_norm=True,
+            residual=True, edge_feat=True, training=True, p=""):
+    """PNANet.forward, `pe_init='lap_pe'`, no LSPE, gru=False (GraphPrediction/nets/ZINC_graph_regression/pna_net.py:116-167):
+    h = embedding_h(atom) + embedding_p(pos_enc); e = embedding_e(bond); L x PNALayer; readout; MLPReadout."""
+    h = sd[p + "embedding_h.weight"][h_idx] + F.linear(pos_enc, sd[p + "embedding_p.weight"], sd[p + "embedding_p.bias"])
+    e = sd[p + "embedding_e.weight"][e_idx] if edge_feat else None
+    for l in range(n_layers):
+        div = divide_input_first if l < n_layers - 1 else divide_input_last
+        h = pna_layer(h, e, src, dst, snorm_n, sd, f"{p}layers.{l}.", towers, div, avg_d_log, graph_norm, batch_norm,
+                      residual, edge_feat, training)
+    n = torch.as_tensor(num_nodes_per_graph)
+    seg = torch.repeat_interleave(torch.arange(n.numel()), n)
+    hg = torch.zeros(n.numel(), h.shape[1], dtype=h.dtype).index_add_(0, seg, h)
+    if readout != "sum":
+        hg = hg / n.to(h.dtype).clamp(min=1).unsqueeze(1)
+    y, L = hg, 2
+    for l in range(L):
+        y = _relu(F.linear(y, sd[f"{p}MLP_layer.FC_layers.{l}.weight"], sd[f"{p}MLP_layer.FC_layers.{l}.bias"]))
+    return F.linear(y, sd[f"{p}MLP_layer.FC_layers.{L}.weight"], sd[f"{p}MLP_layer.FC_layers.{L}.bias"])
+
+
 def handle_lap(pos_enc, num_nodes_per_graph, lap_method, sign_flip=None):
     """The positional-encoding baselines of train/train_ZINC_graph_regression.py:12-47 other than `sign_inv`:
     'sign_flip' (random column signs; the caller passes the draw), 'abs_val', 'canonical' (per graph and column:

@@ -25,13 +25,20 @@ class BatchedGraph:
     def num_nodes(self):
         return int(self._bnn.sum())
 
-    # message passing with the dgl.function builtins (gatedgcn_layer.py:48-53)
+    # message passing with the dgl.function builtins (gatedgcn_layer.py:48-53) or user-defined functions
+    # (pna_layer.py:37-55,65-68: edges.src / edges.dst / edges.data, nodes.mailbox with DGL's degree bucketing)
     def apply_edges(self, func):
+        if callable(func):
+            self.edata.update(func(_EdgeBatch(self)))
+            return
         kind, u, v, out = func
         assert kind == "u_add_v"
         self.edata[out] = self.ndata[u].index_select(0, self.src) + self.ndata[v].index_select(0, self.dst)
 
     def update_all(self, message_func, reduce_func):
+        if callable(reduce_func):
+            self._update_all_udf(message_func, reduce_func)
+            return
         kind, a, b, m_name = message_func
         if kind == "u_mul_e":
             m = self.ndata[a].index_select(0, self.src) * self.edata[b]
@@ -42,6 +49,57 @@ class BatchedGraph:
         rkind, r_in, r_out = reduce_func
         assert rkind == "sum" and r_in == m_name
         self.ndata[r_out] = torch.zeros(self.num_nodes(), *m.shape[1:], dtype=m.dtype).index_add(0, self.dst, m)
+
+
+class _EdgeBatch:
+    def __init__(self, g):
+        self.src = _Gather(g.ndata, g.src)
+        self.dst = _Gather(g.ndata, g.dst)
+        self.data = g.edata
+
+
+class _Gather:
+    def __init__(self, store, index):
+        self.store, self.index = store, index
+
+    def __getitem__(self, key):
+        return self.store[key].index_select(0, self.index)
+
+
+class _NodeBatch:
+    def __init__(self, mailbox):
+        self.mailbox = mailbox
+
+
+def _update_all_udf(self, message_func, reduce_func):
+    """DGL semantics for a user-defined reduce: nodes are bucketed by in-degree D > 0 and the reduce function sees a
+    mailbox [n_D, D, ...] whose messages are in edge-id order; nodes without incoming edges keep zeros."""
+    if callable(message_func):
+        msgs = message_func(_EdgeBatch(self))
+    else:
+        kind, a, _, m_name = message_func
+        assert kind == "copy_u"
+        msgs = {m_name: self.ndata[a].index_select(0, self.src)}
+    N = self.num_nodes()
+    order = torch.sort(self.dst, stable=True).indices            # edges grouped by destination, edge-id order inside
+    deg = torch.bincount(self.dst, minlength=N)
+    start = torch.cumsum(deg, 0) - deg
+    out = {}
+    for D in torch.unique(deg).tolist():
+        if D == 0:
+            continue
+        nodes = torch.nonzero(deg == D).flatten()
+        eids = order[(start[nodes].unsqueeze(1) + torch.arange(D).unsqueeze(0)).flatten()]
+        mailbox = {k: v.index_select(0, eids).reshape(nodes.numel(), D, *v.shape[1:]) for k, v in msgs.items()}
+        res = reduce_func(_NodeBatch(mailbox))
+        for k, v in res.items():
+            if k not in out:
+                out[k] = torch.zeros(N, *v.shape[1:], dtype=v.dtype)
+            out[k] = out[k].index_copy(0, nodes, v)
+    self.ndata.update(out)
+
+
+BatchedGraph._update_all_udf = _update_all_udf
 
 
 def _segments(g):

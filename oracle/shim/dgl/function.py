@@ -16,5 +16,9 @@ def copy_e(e, out):
     return ("copy_e", e, None, out)
 
 
+def copy_u(u, out):
+    return ("copy_u", u, None, out)
+
+
 def sum(msg, out):  # noqa: A001 (dgl's own name)
     return ("sum", msg, out)

@@ -137,6 +137,33 @@ def make_gatedgcn_net():
                 "grads": _grads(net), "state_dict_after": _sd(net)}, os.path.join(OUT, "dgl_gatedgcn_net.pt"))
 
 
+def make_pna_net():
+    """the reference's own PNANet (+ masked_gin sign_inv_net; structure of
+    configs/pna/PNA_ZINC_LapPE_signinv_GIN_mask.json at a small width) on a small seeded batch."""
+    pn = ref_loader.pna_net()
+    import dgl
+    params = dict(num_atom_type=28, num_bond_type=4, hidden_dim=20, out_dim=20, in_feat_dropout=0.0, dropout=0.0, L=3,
+                  readout="sum", graph_norm=True, batch_norm=True, residual=True, aggregators="mean max min std",
+                  scalers="identity amplification attenuation", avg_d={"log": 1.1}, towers=5, divide_input_first=True,
+                  divide_input_last=True, edge_feat=True, edge_dim=8, pretrans_layers=1, posttrans_layers=1, gru=False,
+                  device="cpu", pe_init="lap_pe", lap_method="sign_inv", lap_lspe=False, use_lapeig_loss=False,
+                  lambda_loss=1000, alpha_loss=1e-4, pos_enc_dim=6, sign_inv_net="masked_gin", phi_out_dim=8,
+                  sign_inv_layers=3, sign_inv_activation="relu", pe_aggregate="concat")
+    torch.manual_seed(23)
+    net = pn.PNANet(params)
+    d = synth_batch(6, "zinc", seed=27, k_dgl=params["pos_enc_dim"])
+    g = dgl.BatchedGraph(d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph)
+    n = torch.as_tensor(d.num_nodes_per_graph)
+    snorm_n = (1.0 / n.float().sqrt()).repeat_interleave(n).unsqueeze(1)
+    sd0 = _sd(net)
+    pe = net.sign_inv_net(g, d.pos_enc.unsqueeze(-1)).squeeze(-1)
+    out, _ = net(g, d.x[:, 0], pe, d.edge_attr.reshape(-1), snorm_n)
+    w = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
+    (out * w).sum().backward()
+    torch.save({"params": params, "state_dict": sd0, "data": _data_dict(d), "snorm_n": snorm_n, "w": w, "out": out.detach(),
+                "grads": _grads(net), "state_dict_after": _sd(net)}, os.path.join(OUT, "dgl_pna_net.pt"))
+
+
 def _slim(sd, rows=32):
     """DiscreteEncoder tables have 500 rows per feature (core/model_utils/elements.py:22) of which the ZINC-shape inputs
     touch < 32: keep the fixture small by storing only the first `rows` rows (the tests zero-pad them back)."""
@@ -216,6 +243,7 @@ if __name__ == "__main__":
     make_dgl()
     make_gin_net()
     make_gatedgcn_net()
+    make_pna_net()
     make_zinc_pyg()
     make_eq_deepsets()
     make_ign()

@@ -152,3 +152,23 @@ def test_zinc_pyg_tree_golden(golden_dir):
     (out * g["w"]).sum().backward()
     want = _fatten(g["grads"])
     assert_grads_close({k: v.grad for k, v in sd.items() if k in want}, want, 1e-6, "ZINC tree (self-consistency)")
+
+
+def test_pna_net_golden(golden_dir):
+    """SURVEY 8f rank 4 (oracle side): restatement of the DGL PNANet predictor vs the reference's own output, gradients and
+    BatchNorm running statistics (fixture dgl_pna_net.pt)."""
+    g = _load(golden_dir, "dgl_pna_net.pt")
+    d, prm = Data(**g["data"]), g["params"]
+    sd = _leaf(g["state_dict"])
+    sub = {k[len("sign_inv_net."):]: v for k, v in sd.items() if k.startswith("sign_inv_net.")}
+    pe = restate.masked_gin_deepsigns(d.pos_enc.unsqueeze(-1), d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph, sub,
+                                      prm["sign_inv_layers"], prm["pos_enc_dim"]).squeeze(-1)
+    out = restate.pna_net(d.x[:, 0], pe, d.edge_attr.reshape(-1), d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph,
+                          g["snorm_n"], sd, prm["L"], prm["towers"], prm["avg_d"]["log"], prm["readout"],
+                          prm["divide_input_first"], prm["divide_input_last"])
+    assert_close_rel(out, g["out"], 2e-5, what="PNANet")
+    (out * g["w"]).sum().backward()
+    assert_grads_close({k: v.grad for k, v in sd.items() if not k.endswith(".eps")}, g["grads"], 5e-5, "PNANet")
+    for k, v in g["state_dict_after"].items():
+        if "running_" in k and k.startswith("layers."):
+            torch.testing.assert_close(sd[k], v, rtol=1e-5, atol=1e-6)

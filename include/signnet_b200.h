@@ -193,6 +193,19 @@ int sb_gated_agg_bwd(const float* dh, const float* de, const float* Bh, const fl
                      const float* ssh, const int64_t* edge_index, const int32_t* in_ptr, const int32_t* in_eid,
                      const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_eid, int64_t N, int64_t E,
                      int32_t ld, float* dBh, float* dDh, float* dEh, float* dCe, void* stream);
+/* ---- K12: multi-aggregator reduction of the PNA predictor (GraphPrediction/layers/pna_layer.py:37-68 pretrans_edges +
+ * update_all(reduce_func_for_h); pna_utils.py:12-31 aggregators, :73-84 scalers).  Message of edge k: j -> i is
+ * (U[j] + V[i]) + Q[k] (the pre-transformation Linear split by input block).  Z [N, ldz >= 13 C], tower-major:
+ * Z[i, t*13*tin + (0..tin)] = h[i, t*tin + .], then for scaler s in (identity, amplification, attenuation) and
+ * aggregator a in (mean, max, min, std): Z[i, t*13*tin + tin + (s*4 + a)*tin + j].  avg_log = net_params['avg_d']['log'].
+ * Backward: dU, dV [N, ld], dQ [E, ld], dh [N, ldh] from dZ (max / min route to the first edge attaining them). */
+int sb_pna_agg_fwd(const float* U, const float* V, const float* Q, const float* h, const int32_t* in_ptr,
+                   const int32_t* in_src, const int32_t* in_eid, int64_t N, int32_t C, int32_t tin, int64_t ld,
+                   int64_t ldh, int64_t ldz, float avg_log, float* Z, void* stream);
+int sb_pna_agg_bwd(const float* dZ, const float* U, const float* V, const float* Q, const int32_t* in_ptr,
+                   const int32_t* in_src, const int32_t* in_eid, const int32_t* out_ptr, const int32_t* out_eid,
+                   int64_t N, int32_t C, int32_t tin, int64_t ld, int64_t ldh, int64_t ldz, float avg_log, float* dU,
+                   float* dV, float* dQ, float* dh, void* stream);
 /* K11: the `canonical` sign convention of train/train_ZINC_graph_regression.py:26-42 (PE baseline): per graph and
  * column flip the sign when the column has fewer non-negative than negative entries or less non-negative mass. */
 int sb_canonical_sign(const float* pe, int64_t ldp, const int32_t* graph_ptr, int64_t B, int32_t k, float* out,

@@ -39,6 +39,8 @@ _SIGNATURES = {
     "sb_gine_agg_bwd": "pppp" + "pppp" + "lli" + "ppp" + "p",
     "sb_gated_agg_fwd": "ppppp" + "ppp" + "li" + "pppp" + "p",
     "sb_gated_agg_bwd": "pppppp" + "p" + "ppppp" + "lli" + "pppp" + "p",
+    "sb_pna_agg_fwd": "pppp" + "ppp" + "lii" + "lll" + "f" + "p" + "p",
+    "sb_pna_agg_bwd": "pppp" + "ppp" + "pp" + "lii" + "lll" + "f" + "pppp" + "p",
     "sb_canonical_sign": "plp" + "li" + "pl" + "p",
     "sb_segment_pool_fwd": "plp" + "iii" + "pl" + "p",
     "sb_segment_pool_bwd": "plpp" + "lii" + "pl" + "p",

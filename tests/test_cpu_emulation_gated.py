@@ -6,50 +6,14 @@ their SOURCE TEXT thread by thread under a tiny prelude that defines threadIdx /
 execution of their indexing and arithmetic.  This is test infrastructure for a kernel file that was written after the
 round's GPU budget was spent; it is not a CPU path of the product (nothing in signnet_basisnet_b200/ can reach it)."""
 import ctypes
-import os
-import re
-import shutil
-import subprocess
 
 import pytest
 import torch
 
+import cpu_emulation
+from cpu_emulation import stable_csr as _stable_csr
 from signnet_basisnet_b200.synth import synth_batch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PRELUDE = r"""
-#include <cmath>
-#include <cstdint>
-struct float4 { float x, y, z, w; };
-static inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
-struct uint3_ { unsigned x, y, z; };
-static uint3_ threadIdx, blockIdx, blockDim, gridDim;
-#define __global__
-#define __device__
-#define __forceinline__ inline
-#define __restrict__
-#define __launch_bounds__(...)
-template <class T> static inline T __ldg(const T* p) { return *p; }
-static inline float __fadd_rn(float a, float b) { return a + b; }
-static inline float __fmul_rn(float a, float b) { return a * b; }
-static inline float __fdiv_rn(float a, float b) { return a / b; }
-static inline float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-static inline void stg4_stream(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-// broadcast from lane 0 only (the one pattern canonical_sign_kernel uses): lanes run in order 0..31, so lane 0 has
-// already deposited its value when the other lanes of the warp ask for it
-static float shfl_lane0_;
-static inline float __shfl_sync(unsigned, float v, int src_lane) {
-  if (src_lane != 0) __builtin_trap();
-  if ((threadIdx.x & 31) == 0) shfl_lane0_ = v;
-  return shfl_lane0_;
-}
-#define LAUNCH(kernel, grid, ...)                                                       \
-  for (unsigned b_ = 0; b_ < (unsigned)(grid); ++b_)                                    \
-    for (unsigned t_ = 0; t_ < 256; ++t_) {                                             \
-      blockIdx = {b_, 0, 0}; threadIdx = {t_, 0, 0}; blockDim = {256, 1, 1}; gridDim = {(unsigned)(grid), 1, 1};  \
-      kernel(__VA_ARGS__);                                                              \
-    }
-"""
 WRAPPERS = r"""
 extern "C" void emu_fwd(const float* Ah, const float* Bh, const float* Dh, const float* Eh, const float* Ce,
                         const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid, long long N, int ld,
@@ -71,41 +35,13 @@ extern "C" void emu_canonical(const float* pe, long long ldp, const int32_t* gp,
 """
 
 
-def _functions(src, pattern):
-    out = []
-    for m in re.finditer(pattern, src):
-        k = src.index("{", m.start())
-        depth = 0
-        while True:
-            depth += {"{": 1, "}": -1}.get(src[k], 0)
-            if depth == 0:
-                break
-            k += 1
-        out.append(src[m.start():k + 1])
-    return out
-
-
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("g++ not available")
-    src = open(os.path.join(ROOT, "signnet_basisnet_b200", "csrc", "gated.cu")).read()
-    parts = _functions(src, r"__device__ __forceinline__ float gt_sigmoid") + _functions(
-        src, r"__global__ void __launch_bounds__\(256\) (?:gated_agg|canonical_sign)_\w+")
-    assert len(parts) == 5
-    d = tmp_path_factory.mktemp("emu")
-    cpp, so = os.path.join(d, "emu.cpp"), os.path.join(d, "libemu.so")
-    open(cpp, "w").write(PRELUDE + "\n".join(parts) + WRAPPERS)
-    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, cpp], check=True)
-    return ctypes.CDLL(so)
-
-
-def _stable_csr(keys, other, N):
-    """What sb_build_csr produces: rows by `keys`, edge-id order inside a row; (ptr, neighbour, edge id) as int32."""
-    order = torch.sort(keys, stable=True).indices
-    ptr = torch.zeros(N + 1, dtype=torch.int32)
-    ptr[1:] = torch.cumsum(torch.bincount(keys, minlength=N), 0).to(torch.int32)
-    return ptr, other[order].to(torch.int32).contiguous(), order.to(torch.int32).contiguous()
+    lib, n = cpu_emulation.build(str(tmp_path_factory.mktemp("emu")), "gated.cu",
+                                 [r"__device__ __forceinline__ float gt_sigmoid",
+                                  r"__global__ void __launch_bounds__\(256\) (?:gated_agg|canonical_sign)_\w+"], WRAPPERS)
+    assert n == 5
+    return lib
 
 
 @pytest.mark.parametrize("B,C,ld,with_de", [(9, 18, 20, True), (4, 128, 128, True), (6, 67, 68, False)])

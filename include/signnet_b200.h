@@ -206,6 +206,10 @@ int sb_pna_agg_bwd(const float* dZ, const float* U, const float* V, const float*
                    const int32_t* in_src, const int32_t* in_eid, const int32_t* out_ptr, const int32_t* out_eid,
                    int64_t N, int32_t C, int32_t tin, int64_t ld, int64_t ldh, int64_t ldz, float avg_log, float* dU,
                    float* dV, float* dQ, float* dh, void* stream);
+/* element-wise companions of the PNA layer: graph normalisation out[r, :] = x[r, :] * s[r] (pna_layer.py:73-74; its own
+ * backward) and LeakyReLU (mixing network, pna_utils.py FCLayer): g == NULL -> out = leaky_relu(x), else out = g * act'(x) */
+int sb_row_scale(const float* x, const float* s, int64_t M, int64_t ld, float* out, void* stream);
+int sb_leaky_relu(const float* g, const float* x, int64_t n, float slope, float* out, void* stream);
 /* K11: the `canonical` sign convention of train/train_ZINC_graph_regression.py:26-42 (PE baseline): per graph and
  * column flip the sign when the column has fewer non-negative than negative entries or less non-negative mass. */
 int sb_canonical_sign(const float* pe, int64_t ldp, const int32_t* graph_ptr, int64_t B, int32_t k, float* out,

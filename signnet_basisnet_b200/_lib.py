@@ -41,6 +41,8 @@ _SIGNATURES = {
     "sb_gated_agg_bwd": "pppppp" + "p" + "ppppp" + "lli" + "pppp" + "p",
     "sb_pna_agg_fwd": "pppp" + "ppp" + "lii" + "lll" + "f" + "p" + "p",
     "sb_pna_agg_bwd": "pppp" + "ppp" + "pp" + "lii" + "lll" + "f" + "pppp" + "p",
+    "sb_row_scale": "pp" + "ll" + "p" + "p",
+    "sb_leaky_relu": "pp" + "l" + "f" + "p" + "p",
     "sb_canonical_sign": "plp" + "li" + "pl" + "p",
     "sb_segment_pool_fwd": "plp" + "iii" + "pl" + "p",
     "sb_segment_pool_bwd": "plpp" + "lii" + "pl" + "p",

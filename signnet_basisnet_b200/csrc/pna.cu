@@ -165,3 +165,36 @@ extern "C" int sb_pna_agg_bwd(const float* dZ, const float* U, const float* V, c
   SB_CHECK_LAUNCH("sb_pna_agg_bwd(src)");
   return SB_OK;
 }
+
+// ---- element-wise companions of the PNA layer: graph normalisation h * snorm_n (pna_layer.py:73-74) and the
+// LeakyReLU(0.01) of the mixing network (pna_utils.py FCLayer, activation='LeakyReLU').  Thread per element.
+__global__ void __launch_bounds__(256) row_scale_kernel(const float* __restrict__ x, const float* __restrict__ s, long long M,
+                                                        long long ld, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= M * ld) return;
+  out[i] = __fmul_rn(x[i], __ldg(s + i / ld));
+}
+__global__ void __launch_bounds__(256) leaky_relu_kernel(const float* __restrict__ g, const float* __restrict__ x, long long n,
+                                                         float slope, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = g ? g[i] : x[i];          // forward: g == NULL -> act(x); backward: g * act'(x)
+  out[i] = (x[i] > 0.f) ? v : __fmul_rn(v, slope);
+}
+
+/* out[r, :] = x[r, :] * s[r]  (its own backward with the gradient as x) */
+extern "C" int sb_row_scale(const float* x, const float* s, int64_t M, int64_t ld, float* out, void* stream) {
+  SB_CHECK_ARG(M >= 0 && ld >= 1, "sb_row_scale: bad sizes");
+  if (M == 0) return SB_OK;
+  row_scale_kernel<<<(unsigned)sb_ceil_div(M * ld, 256), 256, 0, (cudaStream_t)stream>>>(x, s, M, ld, out);
+  SB_CHECK_LAUNCH("sb_row_scale");
+  return SB_OK;
+}
+/* g == NULL: out = leaky_relu(x, slope);  else: out = g * (x > 0 ? 1 : slope) */
+extern "C" int sb_leaky_relu(const float* g, const float* x, int64_t n, float slope, float* out, void* stream) {
+  SB_CHECK_ARG(n >= 0, "sb_leaky_relu: bad size");
+  if (n == 0) return SB_OK;
+  leaky_relu_kernel<<<(unsigned)sb_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(g, x, n, slope, out);
+  SB_CHECK_LAUNCH("sb_leaky_relu");
+  return SB_OK;
+}

@@ -10,7 +10,7 @@ for m in 5 6 3 4; do
   tail -16 gpurun_out/pair_check_mode$m.log
 done
 SB_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py tests/test_gpu_gatedgcn.py tests/test_gpu_pna.py tests/test_gpu_zinc_tree_golden.py \
-  -m gpu -q -x > gpurun_out/pytest_experimental.log 2>&1; echo "pytest experimental rc=$?"; tail -15 gpurun_out/pytest_experimental.log
+  -m gpu -q > gpurun_out/pytest_experimental.log 2>&1; echo "pytest experimental rc=$?"; tail -15 gpurun_out/pytest_experimental.log
 timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 600 gpurun_out/bench_default.json
 for t in 1 2 3 4; do
   SB_LINEAR_TMA=$t timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_tma$t.json 2> gpurun_out/bench_tma$t.err

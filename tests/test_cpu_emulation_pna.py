@@ -24,14 +24,20 @@ extern "C" void emu_bwd(const float* dZ, const float* U, const float* V, const f
   LAUNCH(pna_agg_bwd_dst_kernel, (N * 32 + 255) / 256, dZ, U, V, Q, in_ptr, in_src, in_eid, N, C, tin, ld, ldh, ldz, avg, dV, dQ, dh)
   LAUNCH(pna_agg_bwd_src_kernel, (N * 32 + 255) / 256, dQ, out_ptr, out_eid, N, ld, dU)
 }
+extern "C" void emu_row_scale(const float* x, const float* s, long long M, long long ld, float* out) {
+  LAUNCH(row_scale_kernel, (M * ld + 255) / 256, x, s, M, ld, out)
+}
+extern "C" void emu_leaky(const float* g, const float* x, long long n, float slope, float* out) {
+  LAUNCH(leaky_relu_kernel, (n + 255) / 256, g, x, n, slope, out)
+}
 """
 
 
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     lib, n = cpu_emulation.build(str(tmp_path_factory.mktemp("emu_pna")), "pna.cu",
-                                 [r"__global__ void __launch_bounds__\(256\) pna_agg_\w+"], WRAPPERS)
-    assert n == 3
+                                 [r"__global__ void __launch_bounds__\(256\) (?:pna_agg|row_scale|leaky_relu)_\w+"], WRAPPERS)
+    assert n == 5
     return lib
 
 
@@ -105,3 +111,17 @@ def test_pna_aggregate_source_emulated(emu, B, C, tin):
         assert not torch.isnan(got).any(), name
         assert float((got[:, :C].double() - want).abs().max()) <= t, (name, float((got[:, :C].double() - want).abs().max()), t)
         assert float(got[:, C:].abs().sum()) == 0, name
+
+
+def test_row_scale_and_leaky_relu_source_emulated(emu):
+    gen = torch.Generator().manual_seed(0)
+    x, s, g = torch.randn(37, 12, generator=gen), torch.rand(37, generator=gen) + 0.1, torch.randn(37, 12, generator=gen)
+    P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    LL, F = ctypes.c_longlong, ctypes.c_float
+    out = torch.full_like(x, float("nan"))
+    emu.emu_row_scale(P(x), P(s), LL(37), LL(12), P(out))
+    assert torch.equal(out, x * s[:, None])
+    emu.emu_leaky(None, P(x), LL(x.numel()), F(0.01), P(out))
+    assert torch.equal(out, torch.nn.functional.leaky_relu(x, 0.01))
+    emu.emu_leaky(P(g), P(x), LL(x.numel()), F(0.01), P(out))
+    assert torch.equal(out, torch.where(x > 0, g, g * 0.01))

@@ -104,6 +104,13 @@ def pna_net():
     return importlib.import_module("nets.ZINC_graph_regression.pna_net")
 
 
+def transformer_net():
+    """-> nets.ZINC_graph_regression.transformer_net of /root/reference/GraphPrediction (sparse graph Transformer)."""
+    _ensure(_SHIM)
+    _ensure(os.path.join(REF_ROOT, "GraphPrediction"))
+    return importlib.import_module("nets.ZINC_graph_regression.transformer_net")
+
+
 def zinc_train_loop():
     """-> train.train_ZINC_graph_regression of /root/reference/GraphPrediction (`handle_lap`: the PE baselines)."""
     _ensure(_SHIM)

@@ -463,6 +463,65 @@ def pna_net(h_idx, pos_enc, e_idx, src, dst, num_nodes_per_graph, snorm_n, sd, n
     return F.linear(y, sd[f"{p}MLP_layer.FC_layers.{L}.weight"], sd[f"{p}MLP_layer.FC_layers.{L}.bias"])
 
 
+def sparse_attention(Qh, Kh, Eh, Vh, src, dst, n_heads):
+    """MultiHeadAttentionLayer.propagate_attention with full_graph=False (GraphPrediction/layers/transformer.py:160-192):
+    per edge k: j -> i and head: a = sum_c K[j] Q[i] E[k] / sqrt(d);  s = exp(clamp(a, -5, 5));
+    out_i = (sum_in s V[j]) / (sum_in s + 1e-6).  [N or E, H*d] in, [N, H*d] out."""
+    N, HD = Qh.shape
+    d = HD // n_heads
+    v = lambda t: t.reshape(-1, n_heads, d)
+    score = (v(Kh).index_select(0, src) * v(Qh).index_select(0, dst)) / (d ** 0.5)
+    score = score * v(Eh)
+    s = torch.exp(score.sum(-1, keepdim=True).clamp(-5, 5))
+    wV = torch.zeros(N, n_heads, d, dtype=Qh.dtype).index_add(0, dst, v(Vh).index_select(0, src) * s)
+    z = torch.zeros(N, n_heads, 1, dtype=Qh.dtype).index_add(0, dst, s)
+    return (wV / (z + 1e-6)).reshape(N, HD)
+
+
+def transformer_layer(h, e, src, dst, sd, p, n_heads, batch_norm=True, residual=True, training=True):
+    """BatchedTransformerLayer.forward as TransformerNet builds it (transformer.py:232-301; transformer_net.py:68-69 passes
+    neither layer_norm nor use_bias, so: no LayerNorm, bias-free Q/K/E/V): attention -> O_h -> residual -> BatchNorm ->
+    FFN (Linear, ReLU, Linear) -> residual -> BatchNorm."""
+    lin = lambda x, n: F.linear(x, sd[f"{p}{n}.weight"], sd.get(f"{p}{n}.bias"))
+    a = sparse_attention(lin(h, "attention_h.Q"), lin(h, "attention_h.K"), lin(e, "attention_h.E"), lin(h, "attention_h.V"),
+                         src, dst, n_heads)
+    x = lin(a, "O_h")
+    if residual:
+        x = h + x
+    if batch_norm:
+        x = _bn(x, sd, f"{p}batch_norm1_h.", training)
+    y = lin(_relu(lin(x, "FFN_h_layer1")), "FFN_h_layer2")
+    if residual:
+        y = x + y
+    if batch_norm:
+        y = _bn(y, sd, f"{p}batch_norm2_h.", training)
+    return y
+
+
+def transformer_net(h_idx, pos_enc, e_idx, src, dst, num_nodes_per_graph, sd, n_layers, n_heads, readout="sum",
+                    pe_aggregate="concat", batch_norm=True, residual=True, training=True, p=""):
+    """TransformerNet.forward, `pe_init='lap_pe'`, no LSPE, full_graph=False, edge_feat=True
+    (GraphPrediction/nets/ZINC_graph_regression/transformer_net.py:89-150)."""
+    h = sd[p + "embedding_h.weight"][h_idx]
+    pp = F.linear(pos_enc, sd[p + "embedding_p.weight"], sd[p + "embedding_p.bias"])
+    if pe_aggregate == "concat":
+        h = F.linear(torch.cat([h, pp], dim=1), sd[p + "pe_proj.weight"], sd[p + "pe_proj.bias"])
+    else:
+        h = h + pp
+    e = sd[p + "embedding_e.weight"][e_idx]
+    for l in range(n_layers):
+        h = transformer_layer(h, e, src, dst, sd, f"{p}layers.{l}.", n_heads, batch_norm, residual, training)
+    n = torch.as_tensor(num_nodes_per_graph)
+    seg = torch.repeat_interleave(torch.arange(n.numel()), n)
+    hg = torch.zeros(n.numel(), h.shape[1], dtype=h.dtype).index_add_(0, seg, h)
+    if readout != "sum":
+        hg = hg / n.to(h.dtype).clamp(min=1).unsqueeze(1)
+    y, L = hg, 2
+    for l in range(L):
+        y = _relu(F.linear(y, sd[f"{p}MLP_layer.FC_layers.{l}.weight"], sd[f"{p}MLP_layer.FC_layers.{l}.bias"]))
+    return F.linear(y, sd[f"{p}MLP_layer.FC_layers.{L}.weight"], sd[f"{p}MLP_layer.FC_layers.{L}.bias"])
+
+
 def handle_lap(pos_enc, num_nodes_per_graph, lap_method, sign_flip=None):
     """The positional-encoding baselines of train/train_ZINC_graph_regression.py:12-47 other than `sign_inv`:
     'sign_flip' (random column signs; the caller passes the draw), 'abs_val', 'canonical' (per graph and column:

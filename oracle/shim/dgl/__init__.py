@@ -16,7 +16,9 @@ class BatchedGraph:
         self._bnn = torch.as_tensor(num_nodes_per_graph)
         self.ndata, self.edata = {}, {}
 
-    def edges(self):
+    def edges(self, form="uv"):
+        if form == "eid":
+            return torch.arange(self.src.numel())
         return self.src, self.dst
 
     def batch_num_nodes(self):
@@ -27,22 +29,28 @@ class BatchedGraph:
 
     # message passing with the dgl.function builtins (gatedgcn_layer.py:48-53) or user-defined functions
     # (pna_layer.py:37-55,65-68: edges.src / edges.dst / edges.data, nodes.mailbox with DGL's degree bucketing)
-    def apply_edges(self, func):
+    def apply_edges(self, func, edges=None):
         if callable(func):
+            if edges is not None:   # the callers here pass every edge id (transformer.py:160-178 with full_graph=False)
+                assert torch.equal(torch.as_tensor(edges), torch.arange(self.src.numel()))
             self.edata.update(func(_EdgeBatch(self)))
             return
         kind, u, v, out = func
         assert kind == "u_add_v"
         self.edata[out] = self.ndata[u].index_select(0, self.src) + self.ndata[v].index_select(0, self.dst)
 
+    def send_and_recv(self, edges, message_func, reduce_func):
+        """transformer.py:182-184 sends along g.edges() = every edge: identical to update_all."""
+        self.update_all(message_func, reduce_func)
+
     def update_all(self, message_func, reduce_func):
         if callable(reduce_func):
             self._update_all_udf(message_func, reduce_func)
             return
         kind, a, b, m_name = message_func
-        if kind == "u_mul_e":
+        if kind in ("u_mul_e", "src_mul_edge"):
             m = self.ndata[a].index_select(0, self.src) * self.edata[b]
-        elif kind == "copy_e":
+        elif kind in ("copy_e", "copy_edge"):
             m = self.edata[a]
         else:
             raise NotImplementedError(kind)

@@ -16,6 +16,14 @@ def copy_e(e, out):
     return ("copy_e", e, None, out)
 
 
+def src_mul_edge(u, e, out):   # pre-0.5 name of u_mul_e (transformer.py:183)
+    return ("src_mul_edge", u, e, out)
+
+
+def copy_edge(e, out):         # pre-0.5 name of copy_e (transformer.py:184)
+    return ("copy_edge", e, None, out)
+
+
 def copy_u(u, out):
     return ("copy_u", u, None, out)
 

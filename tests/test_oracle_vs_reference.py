@@ -301,3 +301,45 @@ def test_pna_net_predictor(towers, divide, readout):
     got = {k2: v.grad for k2, v in sd.items() if v.requires_grad and v.grad is not None and not k2.endswith(".eps")}
     assert set(want) == set(got)
     assert_grads_close(got, want, 5e-5, "pna_net")
+
+
+TRANSFORMER_NET_PARAMS = dict(num_atom_type=28, num_bond_type=4, hidden_dim=16, out_dim=16, n_heads=4, full_graph=False,
+                              in_feat_dropout=0.0, dropout=0.0, L=3, readout="sum", batch_norm=True, layer_norm=True,
+                              residual=True, edge_feat=True, device="cpu", pe_init="lap_pe", lap_method="sign_inv",
+                              lap_lspe=False, use_lapeig_loss=False, lambda_loss=1, alpha_loss=1e-4, pos_enc_dim=6,
+                              sign_inv_net="gin", phi_out_dim=4, sign_inv_layers=3, sign_inv_activation="relu",
+                              pe_aggregate="concat")
+
+
+@pytest.mark.parametrize("pe_aggregate,readout,n_heads", [("concat", "sum", 4), ("add", "mean", 2)])
+def test_transformer_net_predictor(pe_aggregate, readout, n_heads):
+    """SURVEY 8f rank 4 (oracle side only so far): the sparse graph Transformer of Transformer_ZINC_LapPE_signinv_GIN.json
+    (transformer_net.py:89-150, transformer.py:117-301 with full_graph=False) consuming the sign-invariant PE.
+    Reference quirk: TransformerNet never forwards `layer_norm` / `use_bias` to its layers, so there is no LayerNorm and
+    the Q/K/E/V projections have no bias whatever net_params says (transformer_net.py:68-69)."""
+    tn = ref_loader.transformer_net()   # puts the stand-in dgl on sys.path
+    import dgl
+
+    torch.manual_seed(13)
+    params = dict(TRANSFORMER_NET_PARAMS, pe_aggregate=pe_aggregate, readout=readout, n_heads=n_heads)
+    net = tn.TransformerNet(params)
+    k = params["pos_enc_dim"]
+    d = synth_batch(6, "zinc", seed=24, k_dgl=k)
+    g = dgl.BatchedGraph(d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph)
+    sd = _leafify(_clone_sd(net))
+    atoms, bonds = d.x[:, 0], d.edge_attr.reshape(-1)
+    pe = net.sign_inv_net(g, d.pos_enc.unsqueeze(-1)).squeeze(-1)
+    ref, _ = net(g, atoms, pe, bonds, None)
+    pe_o = restate.gin_deepsigns(d.pos_enc.unsqueeze(-1), d.edge_index[0], d.edge_index[1],
+                                 {k2[len("sign_inv_net."):]: v for k2, v in sd.items() if k2.startswith("sign_inv_net.")},
+                                 params["sign_inv_layers"], k).squeeze(-1)
+    out = restate.transformer_net(atoms, pe_o, bonds, d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph, sd,
+                                  params["L"], n_heads, readout, pe_aggregate)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-5)
+    w = torch.randn_like(ref)
+    (ref * w).sum().backward()
+    (out * w).sum().backward()
+    want = {k2: v.grad for k2, v in net.named_parameters() if v.grad is not None}
+    got = {k2: v.grad for k2, v in sd.items() if v.requires_grad and v.grad is not None and not k2.endswith(".eps")}
+    assert set(want) == set(got)   # gamma (full-graph mixing weight) never reaches the output: no gradient on either side
+    assert_grads_close(got, want, 5e-5, "transformer_net")

@@ -210,6 +210,19 @@ int sb_pna_agg_bwd(const float* dZ, const float* U, const float* V, const float*
  * backward) and LeakyReLU (mixing network, pna_utils.py FCLayer): g == NULL -> out = leaky_relu(x), else out = g * act'(x) */
 int sb_row_scale(const float* x, const float* s, int64_t M, int64_t ld, float* out, void* stream);
 int sb_leaky_relu(const float* g, const float* x, int64_t n, float slope, float* out, void* stream);
+/* ---- K13: edge-modulated sparse attention of the graph-Transformer predictor (GraphPrediction/layers/transformer.py:
+ * 160-192, full_graph=False: apply_edges(src_dot_dst, scaling, imp_exp_attn, exp) + 2 x send_and_recv(sum)):
+ * a_k = sum_c ((K[src,c] Q[dst,c]) / sqrt(d)) E[k,c] per head, s = exp(clamp(a, -5, 5)),
+ * out[i] = sum_in(s V[src]) / (sum_in s + 1e-6).  H heads of width d <= 32, H*d <= ld.  araw [E, H] and z [N, H] are kept
+ * for the backward; dKe / dVe [E, ld] are scratch (per-edge contributions summed per source node in CSC order). */
+int sb_edge_attention_fwd(const float* Q, const float* K, const float* Ef, const float* V, const int32_t* in_ptr,
+                          const int32_t* in_src, const int32_t* in_eid, int64_t N, int32_t H, int32_t d, int64_t ld,
+                          float* out, float* araw, float* z, void* stream);
+int sb_edge_attention_bwd(const float* dout, const float* out, const float* Q, const float* K, const float* Ef,
+                          const float* V, const float* araw, const float* z, const int32_t* in_ptr, const int32_t* in_src,
+                          const int32_t* in_eid, const int32_t* out_ptr, const int32_t* out_eid, int64_t N, int32_t H,
+                          int32_t d, int64_t ld, float* dQ, float* dK, float* dE, float* dV, float* dKe, float* dVe,
+                          void* stream);
 /* K11: the `canonical` sign convention of train/train_ZINC_graph_regression.py:26-42 (PE baseline): per graph and
  * column flip the sign when the column has fewer non-negative than negative entries or less non-negative mass. */
 int sb_canonical_sign(const float* pe, int64_t ldp, const int32_t* graph_ptr, int64_t B, int32_t k, float* out,

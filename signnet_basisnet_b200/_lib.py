@@ -43,6 +43,8 @@ _SIGNATURES = {
     "sb_pna_agg_bwd": "pppp" + "ppp" + "pp" + "lii" + "lll" + "f" + "pppp" + "p",
     "sb_row_scale": "pp" + "ll" + "p" + "p",
     "sb_leaky_relu": "pp" + "l" + "f" + "p" + "p",
+    "sb_edge_attention_fwd": "pppp" + "ppp" + "lii" + "l" + "ppp" + "p",
+    "sb_edge_attention_bwd": "pppppp" + "pp" + "ppp" + "pp" + "lii" + "l" + "pppppp" + "p",
     "sb_canonical_sign": "plp" + "li" + "pl" + "p",
     "sb_segment_pool_fwd": "plp" + "iii" + "pl" + "p",
     "sb_segment_pool_bwd": "plpp" + "lii" + "pl" + "p",

@@ -61,7 +61,7 @@ def functions(src, pattern):
 
 
 
-def build(tmp_dir, cu_file, patterns, wrappers):
+def build(tmp_dir, cu_file, patterns, wrappers, defines=""):
     """Extract the functions matching `patterns` from csrc/<cu_file>, append extern "C" `wrappers` (which use LAUNCH)
     and return the loaded shared library."""
     if shutil.which("g++") is None:
@@ -69,7 +69,7 @@ def build(tmp_dir, cu_file, patterns, wrappers):
     src = open(os.path.join(ROOT, "signnet_basisnet_b200", "csrc", cu_file)).read()
     parts = [f for pat in patterns for f in functions(src, pat)]
     cpp, so = os.path.join(tmp_dir, "emu.cpp"), os.path.join(tmp_dir, "libemu.so")
-    open(cpp, "w").write(PRELUDE + "\n".join(parts) + wrappers)
+    open(cpp, "w").write(PRELUDE + defines + "\n" + "\n".join(parts) + "\n" + wrappers)
     subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, cpp], check=True)
     return ctypes.CDLL(so), len(parts)
 

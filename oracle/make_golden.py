@@ -164,6 +164,29 @@ def make_pna_net():
                 "grads": _grads(net), "state_dict_after": _sd(net)}, os.path.join(OUT, "dgl_pna_net.pt"))
 
 
+def make_transformer_net():
+    """the reference's own TransformerNet (+ gin sign_inv_net; structure of
+    configs/transformer/Transformer_ZINC_LapPE_signinv_GIN.json at a small width) on a small seeded batch."""
+    tn = ref_loader.transformer_net()
+    import dgl
+    params = dict(num_atom_type=28, num_bond_type=4, hidden_dim=16, out_dim=16, n_heads=4, full_graph=False,
+                  in_feat_dropout=0.0, dropout=0.0, L=3, readout="sum", batch_norm=True, layer_norm=True, residual=True,
+                  edge_feat=True, device="cpu", pe_init="lap_pe", lap_method="sign_inv", lap_lspe=False,
+                  use_lapeig_loss=False, lambda_loss=1, alpha_loss=1e-4, pos_enc_dim=6, sign_inv_net="gin", phi_out_dim=4,
+                  sign_inv_layers=3, sign_inv_activation="relu", pe_aggregate="concat")
+    torch.manual_seed(29)
+    net = tn.TransformerNet(params)
+    d = synth_batch(6, "zinc", seed=31, k_dgl=params["pos_enc_dim"])
+    g = dgl.BatchedGraph(d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph)
+    sd0 = _sd(net)
+    pe = net.sign_inv_net(g, d.pos_enc.unsqueeze(-1)).squeeze(-1)
+    out, _ = net(g, d.x[:, 0], pe, d.edge_attr.reshape(-1), None)
+    w = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
+    (out * w).sum().backward()
+    torch.save({"params": params, "state_dict": sd0, "data": _data_dict(d), "w": w, "out": out.detach(),
+                "grads": _grads(net), "state_dict_after": _sd(net)}, os.path.join(OUT, "dgl_transformer_net.pt"))
+
+
 def _slim(sd, rows=32):
     """DiscreteEncoder tables have 500 rows per feature (core/model_utils/elements.py:22) of which the ZINC-shape inputs
     touch < 32: keep the fixture small by storing only the first `rows` rows (the tests zero-pad them back)."""
@@ -244,6 +267,7 @@ if __name__ == "__main__":
     make_gin_net()
     make_gatedgcn_net()
     make_pna_net()
+    make_transformer_net()
     make_zinc_pyg()
     make_eq_deepsets()
     make_ign()

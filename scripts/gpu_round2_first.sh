@@ -2,14 +2,14 @@
 # First GPU visit of the next round: everything that was written after round 1's GPU budget ran out.
 #   gpurun --timeout 1500 -- 'bash scripts/gpu_round2_first.sh'
 # 1. the opt-in Linear / wgrad kernels through the C ABI (no torch): correctness vs the default kernel + fp64, timing
-# 2. the gated GPU tests (opt-in kernels, GatedGCN and PNA predictors, PE baselines) and the new ZINC-tree golden test
+# 2. the gated GPU tests (opt-in kernels, GatedGCN, PNA and Transformer predictors, PE baselines) and the new ZINC-tree golden test
 # 3. bench with the default kernels and with each opt-in mode (end-to-end effect)
 mkdir -p gpurun_out
 for m in 5 6 3 4; do
   timeout 120 ./scripts/build/pair_check $m > gpurun_out/pair_check_mode$m.log 2>&1; echo "pair_check $m rc=$?"
   tail -16 gpurun_out/pair_check_mode$m.log
 done
-SB_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py tests/test_gpu_gatedgcn.py tests/test_gpu_pna.py tests/test_gpu_zinc_tree_golden.py \
+SB_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py tests/test_gpu_gatedgcn.py tests/test_gpu_pna.py tests/test_gpu_graph_transformer.py tests/test_gpu_zinc_tree_golden.py \
   -m gpu -q > gpurun_out/pytest_experimental.log 2>&1; echo "pytest experimental rc=$?"; tail -15 gpurun_out/pytest_experimental.log
 timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 600 gpurun_out/bench_default.json
 for t in 1 2 3 4; do

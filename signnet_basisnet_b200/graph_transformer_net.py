@@ -1,0 +1,182 @@
+"""DGL-flavour sparse graph-Transformer predictor consuming the sign-invariant positional encoding —
+the base model of `configs/transformer/Transformer_ZINC_LapPE_signinv_GIN{,_masked}.json`.
+
+Mirrors GraphPrediction/nets/ZINC_graph_regression/transformer_net.py:21-150 (`TransformerNet`, `pe_init='lap_pe'`, no
+LSPE, `full_graph=False`, `edge_feat=True`) and layers/transformer.py:117-301 (`MultiHeadAttentionLayer`,
+`BatchedTransformerLayer`): same `net_params` keys, same state_dict keys (`layers.{l}.gamma` and its alias
+`layers.{l}.attention_h.gamma`, `layers.{l}.attention_h.{Q,K,E,V}.weight`, `layers.{l}.O_h.*`,
+`layers.{l}.batch_norm{1,2}_h.*`, `layers.{l}.FFN_h_layer{1,2}.*`, `embedding_{h,p,e}`, `pe_proj`, `MLP_layer.FC_layers.*`,
+`sign_inv_net.*`), `forward(g, h, p, e, snorm_n) -> (scores, g)`.  Reference quirk kept: TransformerNet never forwards
+`layer_norm` / `use_bias` to its layers (transformer_net.py:68-69), so there is no LayerNorm and Q/K/E/V have no bias.
+
+Kernels: Q/K/V/E, O_h and the FFN = sb_linear_fwd / sb_linear_wgrad; the dgl message passing
+(apply_edges x 4 + send_and_recv x 2) = ONE fused sb_edge_attention_fwd/bwd (csrc/graph_attention.cu); BatchNorm (+ the
+residual that precedes it, added by sb_affine_act_res) = the BatchNorm kernels of phi; read-out = sb_segment_pool.
+STATUS: oracle side pinned against the reference class (oracle/restate.transformer_net); csrc/graph_attention.cu is
+checked by CPU emulation (tests/test_cpu_emulation_attention.py); this module has not run on a GPU yet
+(tests/test_gpu_graph_transformer.py, gated behind SB_EXPERIMENTAL=1).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ._lib import counted_call as _call, ptr as _p
+from .deepsigns import _graph_index, get_sign_inv_net
+from .functional import add_rows, batch_norm_act, linear
+from .gin_net import MLPReadout
+from .layout import pad4
+from .model import EmbeddingSumFn, Linear2Fn, SegmentPoolFn
+
+
+class EdgeAttentionFn(torch.autograd.Function):
+    """(Q, K, V [N, ld], E [E, ld]) -> out [N, ld]; transformer.py:160-192 with full_graph=False."""
+
+    @staticmethod
+    def forward(ctx, Q, K, Ef, V, gi, H, d):
+        Q, K, Ef, V = (t.contiguous() for t in (Q, K, Ef, V))
+        N, ld = Q.shape
+        if Ef.shape[0] != gi.E or N != gi.N or Ef.shape[1] != ld or K.shape != Q.shape or V.shape != Q.shape:
+            raise ValueError("edge attention: node / edge tensors do not match the graph")
+        dev = Q.device
+        out = torch.empty(N, ld, dtype=torch.float32, device=dev)
+        araw = torch.empty(gi.E, H, dtype=torch.float32, device=dev)
+        z = torch.empty(N, H, dtype=torch.float32, device=dev)
+        _call("sb_edge_attention_fwd", _p(Q), _p(K), _p(Ef), _p(V), _p(gi.in_ptr), _p(gi.in_src), _p(gi.in_eid), N, H, d, ld,
+              _p(out), _p(araw), _p(z))
+        ctx.save_for_backward(Q, K, Ef, V, out, araw, z)
+        ctx.cfg = (gi, H, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        Q, K, Ef, V, out, araw, z = ctx.saved_tensors
+        gi, H, d = ctx.cfg
+        N, ld = Q.shape
+        dev = Q.device
+        dout = dout.contiguous()
+        dQ, dK, dV = (torch.empty(N, ld, dtype=torch.float32, device=dev) for _ in range(3))
+        dE, dKe, dVe = (torch.empty(gi.E, ld, dtype=torch.float32, device=dev) for _ in range(3))
+        _call("sb_edge_attention_bwd", _p(dout), _p(out), _p(Q), _p(K), _p(Ef), _p(V), _p(araw), _p(z), _p(gi.in_ptr),
+              _p(gi.in_src), _p(gi.in_eid), _p(gi.out_ptr), _p(gi.out_eid), N, H, d, ld, _p(dQ), _p(dK), _p(dE), _p(dV),
+              _p(dKe), _p(dVe))
+        return dQ, dK, dE, dV, None, None, None
+
+
+class MultiHeadAttentionLayer(nn.Module):
+    def __init__(self, gamma, in_dim, out_dim, num_heads, full_graph, use_bias, attention_for):
+        super().__init__()
+        if full_graph:
+            raise NotImplementedError("full_graph=True (SAN-style fake edges) is not built: every shipped sign_inv "
+                                      "configuration sets full_graph=false")
+        self.out_dim, self.num_heads, self.full_graph = out_dim, num_heads, full_graph
+        self.attention_for = attention_for
+        self.gamma = gamma   # the layer's Parameter, registered here as well (state_dict alias `attention_h.gamma`)
+        self.Q = nn.Linear(in_dim, out_dim * num_heads, bias=use_bias)
+        self.K = nn.Linear(in_dim, out_dim * num_heads, bias=use_bias)
+        self.E = nn.Linear(in_dim, out_dim * num_heads, bias=use_bias)
+        self.V = nn.Linear(in_dim, out_dim * num_heads, bias=use_bias)
+
+    def forward_rows(self, gi, h, e):
+        ld = pad4(self.out_dim * self.num_heads)
+        lin = lambda x, m: linear(x, m.weight, m.bias, ld)
+        return EdgeAttentionFn.apply(lin(h, self.Q), lin(h, self.K), lin(e, self.E), lin(h, self.V), gi, self.num_heads,
+                                     self.out_dim)
+
+
+class BatchedTransformerLayer(nn.Module):
+    def __init__(self, in_dim, out_dim, num_heads, full_graph, dropout=0.0, layer_norm=False, batch_norm=True,
+                 residual=True, use_bias=False, use_edge=False):
+        super().__init__()
+        if dropout != 0 or layer_norm or not use_edge or not batch_norm:
+            raise NotImplementedError("BatchedTransformerLayer: only the form TransformerNet builds (dropout 0, no "
+                                      "LayerNorm, BatchNorm, edge-modulated attention) is built")
+        self.in_channels, self.out_channels, self.num_heads = in_dim, out_dim, num_heads
+        self.residual, self.batch_norm, self.layer_norm = residual, batch_norm, layer_norm
+        self.gamma = nn.Parameter(torch.FloatTensor([0.1]))
+        self.attention_h = MultiHeadAttentionLayer(self.gamma, in_dim, out_dim // num_heads, num_heads, full_graph, use_bias,
+                                                   attention_for="h")
+        self.O_h = nn.Linear(out_dim, out_dim)
+        self.batch_norm1_h = nn.BatchNorm1d(out_dim)
+        self.FFN_h_layer1 = nn.Linear(out_dim, out_dim * 2)
+        self.FFN_h_layer2 = nn.Linear(out_dim * 2, out_dim)
+        self.batch_norm2_h = nn.BatchNorm1d(out_dim)
+
+    def forward_rows(self, gi, h, e):
+        """h [N, pad4(in)], e [E, pad4(in)] -> [N, pad4(out)]."""
+        ld = pad4(self.out_channels)
+        a = self.attention_h.forward_rows(gi, h, e)
+        x = linear(a, self.O_h.weight, self.O_h.bias, ld)
+        if self.residual:
+            x = add_rows(h, x)                                                          # transformer.py:262-263
+        x = batch_norm_act(x, self.batch_norm1_h, self.training, relu=False)            # :268-269
+        y = linear(x, self.FFN_h_layer1.weight, self.FFN_h_layer1.bias, pad4(2 * self.out_channels), relu=True)
+        y = linear(y, self.FFN_h_layer2.weight, self.FFN_h_layer2.bias, ld)
+        if self.residual:
+            y = add_rows(x, y)                                                          # :279-280
+        return batch_norm_act(y, self.batch_norm2_h, self.training, relu=False)         # :285-286
+
+    def forward(self, g, h, p, e):
+        return self.forward_rows(_graph_index(g, h.device), h, e)[:, :self.out_channels], None
+
+
+class TransformerNet(nn.Module):
+    def __init__(self, net_params):
+        super().__init__()
+        hidden_dim, out_dim = net_params["hidden_dim"], net_params["out_dim"]
+        n_heads, full_graph = net_params["n_heads"], net_params["full_graph"]
+        self.n_layers = net_params["L"]
+        self.readout = net_params["readout"]
+        self.batch_norm = net_params["batch_norm"]
+        self.layer_norm = net_params["layer_norm"]     # read and ignored, like the reference (transformer_net.py:68-69)
+        self.residual = net_params["residual"]
+        self.edge_feat = net_params["edge_feat"]
+        self.device = net_params["device"]
+        self.pe_init = net_params["pe_init"]
+        self.lap_method = net_params["lap_method"]
+        self.lap_lspe = net_params["lap_lspe"]
+        self.use_lapeig_loss = net_params["use_lapeig_loss"]
+        self.lambda_loss, self.alpha_loss = net_params["lambda_loss"], net_params["alpha_loss"]
+        self.pos_enc_dim = net_params["pos_enc_dim"]
+        self.pe_aggregate = net_params["pe_aggregate"]
+        if self.pe_init != "lap_pe" or self.lap_lspe:
+            raise NotImplementedError("TransformerNet on the B200 path is the `pe_init='lap_pe'`, no-LSPE predictor")
+        if not self.edge_feat or self.use_lapeig_loss:
+            raise NotImplementedError("TransformerNet: edge_feat=False / lapeig loss are not built")
+        if net_params["in_feat_dropout"] != 0 or net_params["dropout"] != 0:
+            raise NotImplementedError("dropout is 0.0 in every shipped sign_inv configuration")
+        self.embedding_p = nn.Linear(self.pos_enc_dim, hidden_dim)
+        self.embedding_h = nn.Embedding(net_params["num_atom_type"], hidden_dim)
+        self.embedding_e = nn.Embedding(net_params["num_bond_type"], hidden_dim)
+        mk = lambda o: BatchedTransformerLayer(hidden_dim, o, n_heads, full_graph, use_edge=self.edge_feat)
+        self.layers = nn.ModuleList([mk(hidden_dim) for _ in range(self.n_layers - 1)] + [mk(out_dim)])
+        self.MLP_layer = MLPReadout(out_dim, 1)
+        self.hidden_dim, self.out_dim = hidden_dim, out_dim
+        self.g = None
+        if self.lap_method == "sign_inv":
+            self.sign_inv_net = get_sign_inv_net(net_params)
+        if self.pe_aggregate == "concat":
+            self.pe_proj = nn.Linear(2 * hidden_dim, hidden_dim)
+
+    def forward(self, g, h, p, e, snorm_n=None):
+        if not (torch.is_tensor(h) and h.is_cuda):
+            raise ValueError("TransformerNet inputs must be CUDA tensors (no CPU fallback)")
+        gi = _graph_index(g, h.device)
+        hd = self.hidden_dim
+        x = EmbeddingSumFn.apply(h.to(torch.int64), self.embedding_h.weight)
+        pp = linear(p.reshape(p.shape[0], -1).contiguous(), self.embedding_p.weight, self.embedding_p.bias, pad4(hd))
+        if self.pe_aggregate == "concat":
+            x = Linear2Fn.apply(x, pp, self.pe_proj.weight, self.pe_proj.bias, hd, hd)
+        else:
+            x = add_rows(x, pp)
+        ee = EmbeddingSumFn.apply(e.reshape(-1).to(torch.int64), self.embedding_e.weight)
+        for layer in self.layers:
+            x = layer.forward_rows(gi, x, ee)
+        if self.readout == "max":
+            raise NotImplementedError("max readout is not built (no shipped configuration selects it)")
+        hg = SegmentPoolFn.apply(x, gi, self.out_dim, self.readout != "sum")
+        self.g = g
+        return self.MLP_layer(hg), g
+
+    def loss(self, scores, targets):
+        return torch.nn.functional.l1_loss(scores, targets)

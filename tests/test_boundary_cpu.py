@@ -95,7 +95,7 @@ def test_alchemy_config_parameter_count():
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
-@pytest.mark.parametrize("which", ["gin_deepsigns", "masked_gin_deepsigns", "gin_net", "gatedgcn_net", "gatedgcn_net_add", "pna_net",
+@pytest.mark.parametrize("which", ["gin_deepsigns", "masked_gin_deepsigns", "gin_net", "gatedgcn_net", "gatedgcn_net_add", "pna_net", "transformer_net",
                                    "ign2to1", "ign_basis_inv", "eq_deepsets"])
 def test_state_dict_matches_reference_other_trees(which):
     """DGL and LearningFilters trees (rows a9-a11, a13-a15): same parameter / buffer names and shapes as the reference's
@@ -135,6 +135,14 @@ def test_state_dict_matches_reference_other_trees(which):
                    lambda_loss=1000, alpha_loss=1e-4, pos_enc_dim=5, sign_inv_net="masked_gin", phi_out_dim=4,
                    sign_inv_layers=3, sign_inv_activation="relu", pe_aggregate="concat")
         ref, mine = ref_loader.pna_net().PNANet(prm), PNANet(prm)
+    elif which == "transformer_net":
+        from signnet_basisnet_b200.graph_transformer_net import TransformerNet
+        prm = dict(num_atom_type=28, num_bond_type=4, hidden_dim=16, out_dim=16, n_heads=4, full_graph=False,
+                   in_feat_dropout=0.0, dropout=0.0, L=3, readout="sum", batch_norm=True, layer_norm=True, residual=True,
+                   edge_feat=True, device="cpu", pe_init="lap_pe", lap_method="sign_inv", lap_lspe=False,
+                   use_lapeig_loss=False, lambda_loss=1, alpha_loss=1e-4, pos_enc_dim=5, sign_inv_net="gin", phi_out_dim=4,
+                   sign_inv_layers=3, sign_inv_activation="relu", pe_aggregate="concat")
+        ref, mine = ref_loader.transformer_net().TransformerNet(prm), TransformerNet(prm)
     elif which == "ign2to1":
         from signnet_basisnet_b200.basisnet import IGN2to1
         ign, _ = ref_loader.learningfilters()
@@ -192,7 +200,7 @@ def test_gnn_model_loader_mirrors_load_net():
                pos_enc_dim=5, sign_inv_net="masked_gin", phi_out_dim=4, sign_inv_layers=2, sign_inv_activation="relu",
                pe_aggregate="add")
     assert isinstance(gnn_model("GIN", prm), GINNet) and isinstance(gnn_model("GatedGCN", prm), GatedGCNNet)
-    for name in ("GAT", "Transformer"):
+    for name in ("GAT",):
         with pytest.raises(NotImplementedError):
             gnn_model(name, prm)
     with pytest.raises(KeyError):

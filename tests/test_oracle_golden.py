@@ -172,3 +172,23 @@ def test_pna_net_golden(golden_dir):
     for k, v in g["state_dict_after"].items():
         if "running_" in k and k.startswith("layers."):
             torch.testing.assert_close(sd[k], v, rtol=1e-5, atol=1e-6)
+
+
+def test_transformer_net_golden(golden_dir):
+    """SURVEY 8f rank 4 (oracle side): restatement of the DGL sparse graph Transformer vs the reference's own output,
+    gradients and BatchNorm running statistics (fixture dgl_transformer_net.pt)."""
+    g = _load(golden_dir, "dgl_transformer_net.pt")
+    d, prm = Data(**g["data"]), g["params"]
+    sd = _leaf(g["state_dict"])
+    sub = {k[len("sign_inv_net."):]: v for k, v in sd.items() if k.startswith("sign_inv_net.")}
+    pe = restate.gin_deepsigns(d.pos_enc.unsqueeze(-1), d.edge_index[0], d.edge_index[1], sub, prm["sign_inv_layers"],
+                               prm["pos_enc_dim"]).squeeze(-1)
+    out = restate.transformer_net(d.x[:, 0], pe, d.edge_attr.reshape(-1), d.edge_index[0], d.edge_index[1],
+                                  d.num_nodes_per_graph, sd, prm["L"], prm["n_heads"], prm["readout"], prm["pe_aggregate"])
+    assert_close_rel(out, g["out"], 2e-5, what="TransformerNet")
+    (out * g["w"]).sum().backward()
+    assert_grads_close({k: v.grad for k, v in sd.items() if not k.endswith(".eps") and v.grad is not None}, g["grads"],
+                       5e-5, "TransformerNet")
+    for k, v in g["state_dict_after"].items():
+        if "running_" in k and k.startswith("layers."):
+            torch.testing.assert_close(sd[k], v, rtol=1e-5, atol=1e-6)

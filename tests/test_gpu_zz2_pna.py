@@ -1,6 +1,6 @@
 """PNA predictor on the GPU against the reference's own output / gradients
 (tests/golden/dgl_pna_net.pt) and the CPU oracle.  csrc/pna.cu and signnet_basisnet_b200/pna_net.py were written after the
-round's GPU budget was spent: like the other not-yet-run pieces these tests need SB_EXPERIMENTAL=1; the kernels' source
+round's GPU budget was spent: like the other not-yet-run pieces these tests run last in the GPU session as non-strict xfail; the kernels' source
 is checked on the CPU by tests/test_cpu_emulation_pna.py and the oracle by tests/test_oracle_vs_reference.py."""
 import os
 
@@ -11,8 +11,10 @@ import restate
 from helpers import assert_close_rel, assert_grads_close
 from signnet_basisnet_b200.synth import Data, synth_batch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SB_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set SB_EXPERIMENTAL=1")]
+# Written after round 1's last GPU visit.  The kernels involved are plain streaming kernels (no barriers, no tensor cores:
+# nothing that can hang), their source is emulated on the CPU and the module wiring is dry-run, so the tests are allowed
+# to run - LAST in the session (file name) and as non-strict xfail: XPASS = parity observed, XFAIL = needs work, never red.
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet observed on a GPU (XPASS = parity holds)")]
 DEV = "cuda"
 
 
@@ -81,7 +83,7 @@ def test_pna_net_golden(golden_dir):
     pe = handle_lap(net, d.pos_enc, G, DEV)
     out, g_ret = net(G, d.x[:, 0], pe, d.edge_attr.reshape(-1), g["snorm_n"].to(DEV))
     assert g_ret is G and out.shape == g["out"].shape
-    assert_close_rel(out.cpu(), g["out"], 5e-5, what="PNANet vs reference")
+    assert_close_rel(out.detach().cpu(), g["out"], 5e-5, what="PNANet vs reference")
     (out * g["w"].to(DEV)).sum().backward()
     got = {k: p.grad.cpu() for k, p in net.named_parameters() if p.grad is not None}
     assert set(got) == set(g["grads"])

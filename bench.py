@@ -5,11 +5,13 @@
     python bench.py --impl reference --steps K --warmup W    # the reference's arithmetic on the host CPU (oracle port)
 
 One JSON line on stdout (rank 0).  A "step" = zero_grad -> SignNetGNN(data) -> L1 loss -> backward on one batch of
-`--batch` graphs per GPU (weak scaling); with N > 1 the flat fp32 gradient buffer is all-reduced over NCCL every step.
+`--batch` graphs per GPU (weak scaling); with N > 1 the flat fp32 gradient buffer is all-reduced over NCCL every step
+(bucketed, overlapped with the backward) and the line also carries a `strong` sub-record: BASELINE.json configs[3] as
+written, ONE global batch of `--batch` graphs sharded over the N GPUs (ddp.shard_batch).
   value        device-resident: inputs already in HBM, CUDA events around K steps, max over ranks
   e2e          through the public module API from pinned HOST buffers: H2D of the batch + step + D2H of the loss
   roofline     phi GIN-aggregate kernel (K1): algorithmic bytes / CUDA-event duration vs measured HBM peak
-  cpu_baseline oracle port (oracle/restate.py) timed on the host cores on a bounded sample of the same workload
+  cpu_baseline oracle port (oracle/restate.py) timed on the host cores on the SAME batch (one step; bounded sample)
 """
 from __future__ import annotations
 
@@ -39,6 +41,14 @@ def make_batch(B, seed):
     g = torch.Generator().manual_seed(seed + 1)
     d.y = torch.randn(B, CFG["n_out"], generator=g)
     return d
+
+
+def workload_config(batch, world, nodes, edges):
+    """The `config` object both arms print (the reference arm runs rank 0's batch of the N = 1 job)."""
+    return {"workload": WORKLOAD, "graphs_per_gpu": batch, "global_batch": batch * world, "nodes_per_gpu": nodes,
+            "edges_per_gpu": edges, "parallelism": f"dp{world}",
+            "l2": "working set per step (>= 0.6 GB per activation tensor) exceeds the 126 MB L2",
+            "weights": "random init (reference default init, seed 0)"}
 
 
 def peaks():
@@ -121,15 +131,17 @@ def run_b200(args):
     host = make_batch(args.batch, seed=1000 + rank).pin_memory()
     resident = host.to(dev)
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.__dict__.values() if torch.is_tensor(v))
+    params = list(model.parameters())
+    use_sync = [True]
 
     def step(data):
-        for p in model.parameters():
+        for p in params:
             p.grad = None
         data.__dict__.pop("_b200_graph_index", None)  # every step is a new batch: bookkeeping is part of the path
         out = model(data)
         loss = (out - data.y).abs().mean()
         loss.backward()
-        if sync is not None:
+        if sync is not None and use_sync[0]:
             sync.allreduce()
         return loss
 
@@ -186,6 +198,28 @@ def run_b200(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    # N > 1: (a) what the gradient exchange costs after overlap = step time with it minus step time without it;
+    # (b) strong scaling, BASELINE.json configs[3] as written: ONE global batch of --batch graphs sharded over the GPUs
+    comm = strong = None
+    if world > 1:
+        use_sync[0] = False
+        ms_local = timed(lambda: step(resident), args.steps)
+        use_sync[0] = True
+        comm = {"collective": "ncclAllReduce(avg) of one flat fp32 gradient buffer in buckets on a side stream",
+                "payload_bytes": sync.last_payload_bytes, "bucket_bytes": sync.bucket_bytes(),
+                "exposed_ms_per_step": round((ms - ms_local) / args.steps, 3),
+                "ms_per_step_without_exchange": round(ms_local / args.steps, 3)}
+        from signnet_basisnet_b200.ddp import shard_batch
+
+        shard = shard_batch(make_batch(args.batch, seed=1000), world, rank).to(dev)
+        for _ in range(max(args.warmup, 3)):
+            step(shard)
+        ms_strong = timed(lambda: step(shard), args.steps)
+        strong = {"scaling": "strong", "global_batch": args.batch, "graphs_per_gpu": shard.num_graphs,
+                  "value": round(args.batch * args.steps / (ms_strong * 1e-3), 1), "unit": "graphs/s",
+                  "ms_per_step": round(ms_strong / args.steps, 3),
+                  "note": "same model, same step; rank r runs graphs [r*B/N, (r+1)*B/N) of ONE seeded batch"}
+
     # per-entry-point breakdown with CUDA events on the launching stream (separate pass, not part of `value`)
     _lib.profile_start()
     for _ in range(args.steps):
@@ -205,13 +239,15 @@ def run_b200(args):
     if tag in prof:
         c, t = prof[tag]
         ach = agg_bytes / (t / c * 1e-3) / 1e9
-        traffic = None
+        traffic = traffic_src = None
         tp = os.path.join(ROOT, "profiles", "agg_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = "static: " + tj.get("source", "ncu --set full capture of an earlier run (profiles/)")
         roof = {"kernel": "gin_agg_tma_kernel (phi aggregate, forward)", "bound": "hbm", "achieved": round(ach, 1),
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": traffic, "algorithmic_bytes_per_launch": agg_bytes,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": agg_bytes,
                 "avg_launch_us": round(t / c * 1e3, 1), "launches_per_step": c / args.steps,
                 "slot_rows_R": sl.R, "dense_slot_bytes_per_launch": 2 * 4 * CFG["n_hid"] * 2 * gi.N * sl.k + 16 * gi.E}
         btag = f"sb_gin_agg[ld={CFG['n_hid']},bwd]"
@@ -230,18 +266,18 @@ def run_b200(args):
         "metric": METRIC, "value": round(graphs / (ms * 1e-3), 1), "unit": "graphs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "graphs_per_gpu": args.batch, "global_batch": args.batch * world,
-                   "nodes_per_gpu": gi.N, "edges_per_gpu": gi.E, "parallelism": f"dp{world}",
-                   "l2": "working set per step (>= 0.6 GB per activation tensor) exceeds the 126 MB L2",
-                   "weights": "random init (reference default init, seed 0)"},
+        "config": workload_config(args.batch, world, gi.N, gi.E),
         "e2e": {"value": round(graphs / (ms_e2e * 1e-3), 1), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": launches, "gpu_launches_note": "C-ABI entry-point calls inside the timed region (each "
                                                         "enqueues >= 1 kernel of libsignnet_b200.so)",
         "clocks": clk.summary(), "roofline": roof, "kernels": kernels,
     }
+    if comm is not None:
+        line["grad_exchange"] = comm
+        line["strong"] = strong
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
+        line["cpu_baseline"] = cpu_baseline(args.batch, args.cpu_sample)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -275,21 +311,49 @@ def _oracle_step_fn(B, seed=1000):
     return step
 
 
-def cpu_baseline(B, budget_s=12.0):
-    """Oracle port on the host cores: repeat fwd+bwd steps on B graphs until ~budget_s of CPU work has been timed."""
-    torch.set_num_threads(os.cpu_count() or 1)
-    step = _oracle_step_fn(B)
-    step()  # warm-up
-    n, t0 = 0, time.perf_counter()
-    while True:
+def _time_steps(step, n):
+    t0 = time.perf_counter()
+    for _ in range(n):
         step()
-        n += 1
-        dt = time.perf_counter() - t0
-        if dt >= budget_s or n >= 64:
-            break
-    return {"value": round(B * n / dt, 2), "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"1 warm-up + {n} timed fwd+bwd steps of the same model on {B} ZINC-shape graphs per step "
-                      f"(oracle/restate.py, torch CPU fp32, {dt:.1f} s of CPU work)"}
+    return time.perf_counter() - t0
+
+
+def _phi_only_step_fn(B, seed=1000):
+    """phi(+v) + phi(-v) forward + backward alone (BASELINE.md §3 asks for whole-step AND phi-only graphs/s)."""
+    import restate
+
+    from signnet_basisnet_b200.sign_net import SignNetGNN
+
+    torch.manual_seed(0)
+    model = SignNetGNN(None, None, CFG["n_hid"], CFG["n_out"], CFG["nl_signnet"], CFG["nl_gnn"], flavour=CFG["flavour"])
+    sd = {k[len("sign_net.phi."):]: v.detach().clone() for k, v in model.state_dict().items()
+          if k.startswith("sign_net.phi.")}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    d = make_batch(B, seed)
+    _, eigV = restate.dense_list_evd(d.eigen_values, d.eigen_vectors, d.batch)
+    mask = restate.slot_mask(d.batch, eigV.shape[1])
+
+    def step():
+        for v in sd.values():
+            if v.requires_grad:
+                v.grad = None
+        restate.phi_pm(eigV, d.edge_index, mask, sd, "", CFG["nl_signnet"], True).sum().backward()
+
+    return step
+
+
+def cpu_baseline(B, B_small):
+    """Oracle port on the host cores, same seeded batch as the GPU arm (rank 0): warm-up on a small batch, then ONE
+    timed fwd+bwd step on the B graphs (about 15 s on 16 cores - the bounded sample of the contract)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    _oracle_step_fn(B_small)()          # warm-up: thread pool, allocator, autograd graph code paths
+    dt = _time_steps(_oracle_step_fn(B), 1)
+    return {"value": round(B / dt, 2), "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "graphs_per_step": B,
+            "sample": f"1 warm-up step on {B_small} graphs + 1 timed fwd+bwd step of the same model on the same {B} "
+                      f"ZINC-shape graphs as the GPU arm (oracle/restate.py, torch CPU fp32, {dt:.1f} s of CPU work)"}
 
 
 def run_reference(args):
@@ -297,25 +361,33 @@ def run_reference(args):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    B = args.cpu_sample
+    B = args.batch                      # the SAME 1024-graph batch (seed 1000 = rank 0 of the GPU arm)
     step = _oracle_step_fn(B)
-    for _ in range(max(1, min(args.warmup, 2))):
-        step()
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
+    warm = max(1, min(args.warmup, 1))
+    steps = max(1, min(args.steps, 2))  # ~15 s per step on 16 cores: the whole run stays within a few minutes
+    _time_steps(step, warm)
+    dt = _time_steps(step, steps)
     v = round(B * steps / dt, 2)
-    sample = (f"{steps} timed steps (after warm-up) of fwd+bwd on {B} ZINC-shape graphs per step with the oracle port "
-              f"of the reference (torch CPU fp32, all host threads)")
+    d = make_batch(B, 1000)
+    # secondary figures: phi alone on the same batch, and the small-batch throughput round 1 reported
+    phi_dt = _time_steps(_phi_only_step_fn(B), 1)
+    small = _oracle_step_fn(args.cpu_sample)
+    small()
+    small_dt = _time_steps(small, 3)
+    sample = (f"{steps} timed steps (after {warm} warm-up) of fwd+bwd on the same {B} ZINC-shape graphs as the GPU arm with "
+              f"the oracle port of the reference (torch CPU fp32, all host threads)")
     emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "graphs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-        "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(dt / steps * 1e3, 1),
+        "steps": steps, "warmup": warm, "ms_per_step": round(dt / steps * 1e3, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "graphs_per_step": B},
+        "config": workload_config(B, 1, int(d.batch.numel()), int(d.edge_index.shape[1])),
+        "graphs_per_step": B,
         "cpu_baseline": {"value": v, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": sample},
+                         "graphs_per_step": B, "sample": sample},
+        "phi_only": {"value": round(B / phi_dt, 2), "unit": "graphs/s", "ms_per_step": round(phi_dt * 1e3, 1),
+                     "what": "phi(+v)+phi(-v) forward+backward alone, same batch (BASELINE.md §3)"},
+        "small_batch": {"graphs_per_step": args.cpu_sample, "value": round(args.cpu_sample * 3 / small_dt, 2),
+                        "unit": "graphs/s", "what": "the 64-graph figure round 1 reported, kept for continuity"},
         "e2e": {"value": v, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -349,7 +421,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="graphs per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=64, help="graphs per step of the CPU baseline")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="graphs per step of the CPU warm-up / small-batch figure")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     _quiet_stdout()

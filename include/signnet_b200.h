@@ -119,19 +119,15 @@ int sb_gin_agg_tile_rows(int32_t ld); /* rows per shared-memory tile of the TMA 
 int sb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t w_rs, int64_t w_cs, const float* bias,
                   float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N, int32_t pro, const float* pa,
                   const float* pc, int32_t relu, double* stats, int32_t accumulate, void* stream);
-/* 1: contractions with 16 <= K,N <= 128 run on tcgen05 (3xTF32, linear_tc.cu); 0: fp32 FFMA everywhere.  Returns the
- * previous setting (-1 = not yet decided; env SB_DISABLE_TC=1 also selects FFMA).  Values 2..4 select an EXPERIMENTAL
- * kernel for the fast shapes of sb_linear_fwd (same contract and arithmetic; everything else stays on the default
- * kernels): 2 = CTA pair (linear_tc_pair.cu, env SB_LINEAR_PAIR=1), 3 = TMA-fed operands and TMA stores
- * (linear_tc_tma.cu, env SB_LINEAR_TMA=1), 4 = 3 with the raw tile as the head operand (env SB_LINEAR_TMA=2),
- * 5 / 6 = split weight resident in tensor memory + 7-stage TMA ring (linear_tc_ws.cu, env SB_LINEAR_TMA=3 / 4;
- * 6 = raw heads; compiled, not yet run on a GPU). */
+/* 1 (default): contractions with 16 <= K,N <= 128 run on tcgen05 (3xTF32; linear_tc.cu, wgrad_tc_tma.cu for N = K = 128,
+ * wgrad_tc.cu otherwise); 2: the same with the register-fed wgrad_tc.cu for every weight gradient (A/B switch of the
+ * tests); 0: fp32 FFMA everywhere.  Returns the previous setting (-1 = not yet decided; env SB_DISABLE_TC=1 = 0). */
 int sb_set_tensor_cores(int32_t enable);
-/* Which kernel the last block launch of sb_linear_fwd used: 0 FFMA, 1 tcgen05, 2..4 as above, -1 none yet (the
- * rank-1 / row-dot streaming kernels do not update it).  Diagnostics for the tests and scripts/pair_check.cu. */
+/* Which kernel the last block launch of sb_linear_fwd used: 0 FFMA, 1 tcgen05, -1 none yet (the rank-1 / row-dot
+ * streaming kernels do not update it).  Diagnostics for the tests. */
 int sb_last_linear_kernel(void);
-/* Same for the last block launch of sb_linear_wgrad: 0 FFMA, 1 tcgen05 (wgrad_tc.cu), >= 3 the opt-in TMA-fed variant
- * (wgrad_tc_tma.cu; selected by the same sb_set_tensor_cores values 3..6, N == K == 128 only). */
+/* Same for the last block launch of sb_linear_wgrad: 0 FFMA, 1 tcgen05 register-fed (wgrad_tc.cu), 3 tcgen05 TMA-fed
+ * (wgrad_tc_tma.cu). */
 int sb_last_wgrad_kernel(void);
 /* dw[n*rs + k*cs] (+)= sum gy[., n] * f(x[., k]);  db[n] (+)= sum gy[., n]   (deterministic two-stage reduction) */
 int sb_linear_wgrad(const float* gy, int64_t ldg, const float* x, int64_t ldx, int64_t R, int32_t G, int32_t N,

@@ -261,44 +261,25 @@ int sb_linear_tc_launch(const float* x, int64_t ldx, const float* w, int64_t w_r
                         float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N, int32_t pro,
                         const float* pa, const float* pc, int32_t relu, double* stats, int32_t accumulate,
                         int32_t ycols, cudaStream_t st);
-// CTA-pair variant (linear_tc_pair.cu), opt-in
-int sb_linear_tc_pair_launch(const float* x, int64_t ldx, const float* w, int64_t w_rs, int64_t w_cs,
-                             const float* bias, float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N,
-                             int32_t pro, const float* pa, const float* pc, int32_t relu, double* stats,
-                             int32_t accumulate, int32_t ycols, cudaStream_t st);
-// TMA-fed variant (linear_tc_tma.cu), opt-in
-int sb_linear_tc_tma_launch(const float* x, int64_t ldx, const float* w, int64_t w_rs, int64_t w_cs, const float* bias,
-                            float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N, int32_t pro,
-                            const float* pa, const float* pc, int32_t relu, double* stats, int32_t accumulate,
-                            int32_t ycols, int32_t rawhead, cudaStream_t st);
-// weight-stationary-in-tensor-memory variant (linear_tc_ws.cu), opt-in
-int sb_linear_tc_ws_launch(const float* x, int64_t ldx, const float* w, int64_t w_rs, int64_t w_cs, const float* bias,
-                           float* y, int64_t ldy, int64_t R, int32_t G, int32_t K, int32_t N, int32_t pro,
-                           const float* pa, const float* pc, int32_t relu, double* stats, int32_t accumulate,
-                           int32_t ycols, int32_t rawhead, cudaStream_t st);
-// -1 undecided, 0 FFMA, 1 tcgen05 (default); experimental kernels for the fast shapes of sb_linear_fwd:
-// 2 CTA pair, 3 TMA-fed, 4 TMA-fed with the raw tile as the head operand, 5 / 6 weight in tensor memory (6: raw heads)
+// -1 undecided, 0 FFMA, 1 tcgen05 (default: Linear = linear_tc.cu; weight gradient = the TMA-fed wgrad_tc_tma.cu for
+// N = K = 128, the register-fed wgrad_tc.cu otherwise), 2 = tcgen05 with the register-fed weight gradient everywhere
+// (kept so that tests can compare the two weight-gradient kernels bit for bit).  Round-2 measurements that decided this
+// (profiles/r2a_pair_check_mode*.log): the TMA-fed weight gradient is bit-identical and 17 % faster (278 vs 338 us at the
+// phi size); the CTA-pair, TMA-fed and weight-in-tensor-memory Linear variants were all slower than linear_tc.cu
+// (393 / 310 / 314 vs 292 us) and have been removed.
 static int g_use_tc = -1;
 static int g_last_variant = -1, g_last_wgrad_variant = -1;
 extern "C" int sb_last_linear_kernel(void) { return g_last_variant; }
 extern "C" int sb_last_wgrad_kernel(void) { return g_last_wgrad_variant; }
 extern "C" int sb_set_tensor_cores(int32_t enable) {
   const int old = g_use_tc;
-  g_use_tc = (enable >= 2 && enable <= 6) ? enable : (enable ? 1 : 0);
+  g_use_tc = (enable == 2) ? 2 : (enable ? 1 : 0);
   return old;
 }
 static bool use_tc() {
   if (g_use_tc < 0) {
     const char* e = getenv("SB_DISABLE_TC");
-    const char* p = getenv("SB_LINEAR_PAIR");
-    const char* t = getenv("SB_LINEAR_TMA");
-    g_use_tc = 1;
-    if (p && p[0] == '1') g_use_tc = 2;
-    if (t && t[0] == '1') g_use_tc = 3;
-    if (t && t[0] == '2') g_use_tc = 4;
-    if (t && t[0] == '3') g_use_tc = 5;
-    if (t && t[0] == '4') g_use_tc = 6;
-    if (e && e[0] == '1') g_use_tc = 0;
+    g_use_tc = (e && e[0] == '1') ? 0 : 1;
   }
   return g_use_tc >= 1;
 }
@@ -378,21 +359,9 @@ extern "C" int sb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_
       int rc = SB_ERR_UNSUPPORTED;
       int variant = 0;
       if (use_tc()) {
-        variant = g_use_tc;
-        if (g_use_tc == 2)
-          rc = sb_linear_tc_pair_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro,
-                                        a.pa, a.pc, a.relu, a.stats, a.accumulate, a.ycols, st);
-        if (g_use_tc >= 5)
-          rc = sb_linear_tc_ws_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro,
-                                      a.pa, a.pc, a.relu, a.stats, a.accumulate, a.ycols, g_use_tc == 6, st);
-        else if (g_use_tc >= 3)
-          rc = sb_linear_tc_tma_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro,
-                                       a.pa, a.pc, a.relu, a.stats, a.accumulate, a.ycols, g_use_tc == 4, st);
-        if (rc == SB_ERR_UNSUPPORTED) {
-          variant = 1;
-          rc = sb_linear_tc_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro, a.pa,
-                                   a.pc, a.relu, a.stats, a.accumulate, a.ycols, st);
-        }
+        variant = 1;
+        rc = sb_linear_tc_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro, a.pa,
+                                 a.pc, a.relu, a.stats, a.accumulate, a.ycols, st);
       }
       if (rc == SB_ERR_UNSUPPORTED) variant = 0;
       g_last_variant = variant;
@@ -648,8 +617,7 @@ int sb_wgrad_tc_launch(const float* gy, int64_t ldg, const float* x, int64_t ldx
 
 int sb_wgrad_tc_tma_launch(const float* gy, int64_t ldg, const float* x, int64_t ldx, int64_t R, int32_t G, int32_t N,
                            int32_t K, int32_t pro, const float* pa, const float* pc, float* dw, int64_t dw_rs,
-                           int64_t dw_cs, float* db, int32_t accumulate, float* workspace, int32_t rawhead,
-                           cudaStream_t st);
+                           int64_t dw_cs, float* db, int32_t accumulate, float* workspace, cudaStream_t st);
 
 template <int BN, int BK>
 static int launch_wgrad(WgArgs a, int N, int K, float* dw, long long rs, long long cs, float* db, int accumulate,
@@ -710,10 +678,10 @@ extern "C" int sb_linear_wgrad(const float* gy, int64_t ldg, const float* x, int
       float* dbp = (db && k0 == 0) ? db + n0 : nullptr;
       int rc = SB_ERR_UNSUPPORTED;
       if (use_tc()) {
-        g_last_wgrad_variant = g_use_tc;
-        if (g_use_tc >= 3)   // opt-in TMA-fed variant (N == K == 128 only); raw heads in the modes that use them
+        g_last_wgrad_variant = 3;
+        if (g_use_tc == 1)   // TMA-fed operand ring (N == K == 128 only)
           rc = sb_wgrad_tc_tma_launch(a.g, a.ldg, a.x, a.ldx, a.R, a.G, a.N, a.K, a.pro, a.pa, a.pc, dwp, dw_rs, dw_cs,
-                                      dbp, accumulate, workspace, g_use_tc == 4 || g_use_tc == 6, st);
+                                      dbp, accumulate, workspace, st);
         if (rc == SB_ERR_UNSUPPORTED) {
           g_last_wgrad_variant = 1;
           rc = sb_wgrad_tc_launch(a.g, a.ldg, a.x, a.ldx, a.R, a.G, a.N, a.K, a.pro, a.pa, a.pc, dwp, dw_rs, dw_cs, dbp,

@@ -1,13 +1,15 @@
-// Weight gradient on tcgen05, TMA-fed (opt-in variant of wgrad_tc.cu for N == K == 128 and 16-byte aligned rows).
-// Same arithmetic, MMA order, accumulator, epilogue and deterministic two-stage reduction as wgrad_tc_tma_kernel<FAST>; what
+// Weight gradient on tcgen05, TMA-fed: the DEFAULT kernel for N == K == 128 and 16-byte aligned rows (the phi stack at
+// n_hid = 128); wgrad_tc.cu (register-fed ring) handles every other fast shape.
+// Same arithmetic, MMA order, accumulator, epilogue and deterministic two-stage reduction as wgrad_tc_kernel<FAST>; what
 // changes is how the operand ring is filled: one thread issues tensor-map TMA loads of the raw 32-row chunks of g and x
 // ([32 rows x 32 floats] boxes, SWIZZLE_128B_ATOM_32B = the MN-major tf32 layout the UMMA descriptor names
 // SWIZZLE_128B_BASE32B; rows past the end of a group are zero-filled) straight into the head buffers of a 3-stage ring,
 // up to three chunks (96 KB) ahead of the MMAs, and the 16 worker warps only add the 3xTF32 tails in place (plus the
-// rewritten head where the forward prologue applies, or everywhere when `rawhead` is off).  Motivation and status:
-// DESIGN.md appendix (linear_tc_tma.cu is the same idea for the forward / input-gradient contraction).
+// rewritten heads: `rawhead` - letting the tensor core truncate the raw fp32 word itself - is measured 3 % faster but
+// not bit-identical to wgrad_tc.cu and stays off).
 //
-// STATUS: opt-in (sb_set_tensor_cores(3..6)); compiles for sm_100a, NOT yet run on a GPU.
+// STATUS (round 2, B200): bit-identical to wgrad_tc.cu on every case of scripts/pair_check.cu and tests/test_gpu_wgrad_
+// variants.py; 278 us vs 338 us per launch at the phi size of cfg 4 (profiles/r2a_pair_check_mode3.log).
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -325,8 +327,7 @@ static int wm_make_map(CUtensorMap* tm, const float* base, int64_t ld, int64_t R
 // caller then uses wgrad_tc_kernel (same contract).
 int sb_wgrad_tc_tma_launch(const float* gy, int64_t ldg, const float* x, int64_t ldx, int64_t R, int32_t G, int32_t N,
                            int32_t K, int32_t pro, const float* pa, const float* pc, float* dw, int64_t dw_rs,
-                           int64_t dw_cs, float* db, int32_t accumulate, float* workspace, int32_t rawhead,
-                           cudaStream_t st) {
+                           int64_t dw_cs, float* db, int32_t accumulate, float* workspace, cudaStream_t st) {
   const bool gvec = (ldg % 4 == 0) && ((uintptr_t)gy % 16 == 0);
   const bool xvec = (ldx % 4 == 0) && ((uintptr_t)x % 16 == 0);
   if (K != 128 || N != 128 || G > WM_MAXG || R * G < 4096 || !gvec || !xvec || R >= (1ll << 31)) return SB_ERR_UNSUPPORTED;
@@ -334,7 +335,7 @@ int sb_wgrad_tc_tma_launch(const float* gy, int64_t ldg, const float* x, int64_t
   if (wm_make_map(&tmg, gy, ldg, R, G) != SB_OK || wm_make_map(&tmx, x, ldx, R, G) != SB_OK) return SB_ERR_UNSUPPORTED;
   WgTmaArgs a;
   a.g = gy; a.ldg = ldg; a.x = x; a.ldx = ldx; a.R = R; a.G = G; a.N = N; a.K = K; a.KP = 128;
-  a.pro = pro; a.pa = pa; a.pc = pc; a.rawhead = rawhead;
+  a.pro = pro; a.pa = pa; a.pc = pc; a.rawhead = 0;
   const long long nch = sb_ceil_div(R, WM_ROWS) * G;
   long long grid = sb_num_sms();
   if (grid > nch) grid = nch;

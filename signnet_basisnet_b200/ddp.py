@@ -1,8 +1,15 @@
 """Graph-sharded data parallelism for the SignNet path: one process per GPU, every rank runs the full model on its own
 shard of graphs (no halo, no exchange in the forward: graphs are independent), BatchNorm statistics stay per replica
-(the reference has no SyncBN), and ONE all-reduce of a flat fp32 gradient buffer per step averages the gradients over
-NVLink/NVSwitch.  Parameters the step never touched (e.g. the final norm MaskedMLP allocates but
-skips, masked_layers.py:43,61) contribute zeros, so every rank reduces the same layout.
+(the reference has no SyncBN), and the gradients are averaged over NVLink/NVSwitch by all-reducing ONE flat fp32
+buffer, cut into a few contiguous buckets that are launched on a side stream as soon as their gradients exist, so the
+collective overlaps the rest of the backward.
+
+What is reduced.  Parameters the step never touches - the final norm MaskedMLP allocates but skips
+(masked_layers.py:43,61), and in the GINESignNetPyG tree phi.edge_encoders, eigen_encoder1/2, rho.pos_encoder and nine
+of the ten DiscreteEncoder tables (core/sign_net.py:22,54,90; quirk v) - never receive a gradient; they are found on
+the first step (`p.grad is None` after backward, checked to be the same set on every rank), keep `grad = None` exactly
+as in single-process training (an optimizer skips them) and are not part of the payload: 4.4 MB instead of 38.4 MB for
+the cfg 4 model.
 
 The reference is single-process (no torch.distributed call site anywhere); this file is the multi-GPU row of the hot
 path, not a port of anything.
@@ -41,41 +48,179 @@ def shard_batch(data, world: int, rank: int):
 
 
 class FlatGradAllReduce:
-    """Average gradients across ranks with a single all-reduce of one flat fp32 buffer."""
+    """Average gradients across ranks through one flat fp32 buffer, reduced in `buckets` overlapped pieces.
 
-    def __init__(self, module: torch.nn.Module, world: int | None = None):
+    Usage per step:  zero grads (any way: None, zeros, or not at all when accumulating) -> forward -> backward ->
+    `allreduce()`.  After `allreduce()` every live parameter's `.grad` is a view of the flat buffer holding the
+    average over ranks; untouched parameters keep `.grad = None`.
+
+    Step 1 runs un-overlapped: it discovers which parameters receive gradients and in which order (hooks), checks that
+    every rank found the same set, lays the flat buffer out in that order and cuts it into buckets.  From step 2 on a
+    bucket is packed and all-reduced on a side stream the moment its last gradient has been accumulated.
+    """
+
+    def __init__(self, module: torch.nn.Module, world: int | None = None, buckets: int = 4):
+        self.module = module
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
-        self.numel = sum(p.numel() for p in self.params)
-        p0 = self.params[0]
-        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=p0.device)
-        self.views, off = [], 0
-        for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+        self.n_buckets = max(1, int(buckets))
+        self.device = self.params[0].device
+        self.flat = None            # built after the first backward
+        self.views = {}             # param index -> view of self.flat
+        self.live, self.dead = [], []
+        self._order = []            # param indices in the order their gradients were accumulated (first step)
+        self._bucket_of, self._buckets = {}, []
+        self._pending, self._works = [], []
+        self._side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self._avg_native = self.device.type == "cuda"   # NCCL has ReduceOp.AVG, gloo does not
+        self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
+        self.last_payload_bytes = 0
 
+    # ------------------------------------------------------------------------------------------------- parameters
     def broadcast_parameters(self, src: int = 0):
-        """Make every replica start from rank `src`'s weights and buffers."""
+        """Make every replica start from rank `src`'s parameters AND floating-point buffers (BatchNorm running
+        statistics); integer buffers (num_batches_tracked) are broadcast too."""
         if self.world == 1:
             return
         with torch.no_grad():
-            flat = torch.cat([p.detach().reshape(-1) for p in self.params])
-            dist.broadcast(flat, src)
-            off = 0
-            for p in self.params:
-                p.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
+            tensors = list(self.module.parameters()) + list(self.module.buffers())
+            fl = [t for t in tensors if t.is_floating_point()]
+            if fl:
+                flat = torch.cat([t.detach().reshape(-1).float() for t in fl])
+                dist.broadcast(flat, src)
+                off = 0
+                for t in fl:
+                    t.copy_(flat[off:off + t.numel()].view_as(t))
+                    off += t.numel()
+            for t in tensors:
+                if not t.is_floating_point():
+                    dist.broadcast(t, src)
 
-    def allreduce(self):
-        """Pack (zero-filling untouched parameters) -> all_reduce(sum) -> scale by 1/world -> hand back as .grad."""
+    # ------------------------------------------------------------------------------------------------------ hooks
+    def _make_hook(self, i):
+        def hook(p):
+            if self.flat is None:
+                self._order.append(i)
+                return
+            b = self._bucket_of.get(i)
+            if b is None:
+                return                  # reported by allreduce(): a parameter thought dead received a gradient
+            self._pending[b] -= 1
+            if self._pending[b] == 0 and self.world > 1:
+                self._launch(b)
+        return hook
+
+    def _is_view(self, i):
+        g = self.params[i].grad
+        return g is not None and g.data_ptr() == self.views[i].data_ptr()
+
+    def _launch(self, b):
+        """Pack bucket b (gradients that are not already the flat views) and start its all-reduce."""
+        lo, hi, idx = self._buckets[b]
         with torch.no_grad():
-            self.flat.zero_()
-            have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
-            if have:
-                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+            if self._side is not None:
+                ev = torch.cuda.Event()
+                ev.record()                     # the backward stream: everything this bucket needs has been enqueued
+                ctx = torch.cuda.stream(self._side)
+                self._side.wait_event(ev)
+            else:
+                ctx = _Null()
+            with ctx:
+                dst, src = [], []
+                for i in idx:
+                    g = self.params[i].grad
+                    if g is None:
+                        self.views[i].zero_()   # a live parameter skipped this step: contributes zeros
+                    elif not self._is_view(i):
+                        dst.append(self.views[i])
+                        src.append(g)
+                if dst:
+                    torch._foreach_copy_(dst, src)
+                piece = self.flat[lo:hi]
+                op = dist.ReduceOp.AVG if self._avg_native else dist.ReduceOp.SUM
+                self._works.append(dist.all_reduce(piece, op=op, async_op=True))
+
+    # ------------------------------------------------------------------------------------------------- first step
+    def _build(self):
+        got = [p.grad is not None for p in self.params]
+        if self.world > 1:   # every rank must reduce the same layout
+            m = torch.tensor([1.0 if g else 0.0 for g in got], device=self.device)
+            lo, hi = m.clone(), m.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            if not torch.equal(lo, hi):
+                raise RuntimeError("FlatGradAllReduce: ranks disagree on which parameters receive gradients")
+        seen = set()
+        order = [i for i in self._order if got[i] and not (i in seen or seen.add(i))]
+        order += [i for i, g in enumerate(got) if g and i not in seen]      # (gradients set without the hook firing)
+        self.live, self.dead = order, [i for i, g in enumerate(got) if not g]
+        total = sum(self.params[i].numel() for i in order)
+        self.flat = torch.zeros(max(total, 1), dtype=torch.float32, device=self.device)
+        off, cuts, target, nb = 0, [], total / self.n_buckets, 1
+        self._buckets, cur, lo = [], [], 0
+        for i in order:
+            n = self.params[i].numel()
+            self.views[i] = self.flat[off:off + n].view_as(self.params[i])
+            cur.append(i)
+            off += n
+            if off >= target * nb and nb < self.n_buckets:
+                self._buckets.append((lo, off, cur))
+                cur, lo, nb = [], off, nb + 1
+        if cur:
+            self._buckets.append((lo, off, cur))
+        self._bucket_of = {i: b for b, (_, _, idx) in enumerate(self._buckets) for i in idx}
+        self.last_payload_bytes = 4 * total
+
+    def _arm(self):
+        self._pending = [len(idx) for _, _, idx in self._buckets]
+        self._works = []
+
+    # ----------------------------------------------------------------------------------------------------- public
+    def allreduce(self):
+        """Finish the step's gradient exchange; returns the flat buffer (averaged gradients of the live parameters)."""
+        with torch.no_grad():
+            first = self.flat is None
+            if first:
+                self._build()
+                self._arm()
+            else:
+                for i in self.dead:
+                    if self.params[i].grad is not None:
+                        raise RuntimeError("FlatGradAllReduce: a parameter that had no gradient on the first step "
+                                           "received one now; rebuild the reducer (the flat layout is fixed)")
             if self.world > 1:
-                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-                self.flat.mul_(1.0 / self.world)
-            for v, p in zip(self.views, self.params):
-                p.grad = v
+                for b in range(len(self._buckets)):     # buckets whose hooks did not complete (first step; skipped params)
+                    if first or self._pending[b] > 0:
+                        self._launch(b)
+                for w in self._works:
+                    w.wait()                            # current stream waits for the collective
+                if self._side is not None:
+                    torch.cuda.current_stream().wait_stream(self._side)
+                if not self._avg_native:
+                    self.flat.mul_(1.0 / self.world)
+            else:
+                dst, src = [], []
+                for i in self.live:
+                    g = self.params[i].grad
+                    if g is None:
+                        self.views[i].zero_()
+                    elif not self._is_view(i):
+                        dst.append(self.views[i])
+                        src.append(g)
+                if dst:
+                    torch._foreach_copy_(dst, src)
+            for i in self.live:                         # only now may the step's own gradient tensors be released
+                self.params[i].grad = self.views[i]
+            self._arm()
         return self.flat
+
+    def bucket_bytes(self):
+        return [4 * (hi - lo) for lo, hi, _ in self._buckets]
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

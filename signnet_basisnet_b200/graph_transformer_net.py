@@ -13,8 +13,8 @@ Kernels: Q/K/V/E, O_h and the FFN = sb_linear_fwd / sb_linear_wgrad; the dgl mes
 (apply_edges x 4 + send_and_recv x 2) = ONE fused sb_edge_attention_fwd/bwd (csrc/graph_attention.cu); BatchNorm (+ the
 residual that precedes it, added by sb_affine_act_res) = the BatchNorm kernels of phi; read-out = sb_segment_pool.
 STATUS: oracle side pinned against the reference class (oracle/restate.transformer_net); csrc/graph_attention.cu is
-checked by CPU emulation (tests/test_cpu_emulation_attention.py); this module has not run on a GPU yet
-(tests/test_gpu_zz3_graph_transformer.py, run last in the GPU session as non-strict xfail).
+checked by CPU emulation (tests/test_cpu_emulation_attention.py); GPU parity (kernel vs oracle,
+TransformerNet vs the reference fixture): tests/test_gpu_graph_transformer.py, green on the B200.
 """
 from __future__ import annotations
 

@@ -17,8 +17,8 @@ towers act on disjoint channel slices, so one layer is
     Y = Z blockdiag(W_post)^T + b;  Y *= snorm_n;  BatchNorm (the towers' statistics are per channel, hence one pass)
     out = h + LeakyReLU(Y W_mix^T + b)                                                  sb_linear_fwd, sb_leaky_relu
 STATUS: oracle side pinned against the reference class (oracle/restate.pna_net, fixture tests/golden/dgl_pna_net.pt);
-csrc/pna.cu is checked by CPU emulation (tests/test_cpu_emulation_pna.py); this module has not run on a GPU yet
-(tests/test_gpu_zz2_pna.py, run last in the GPU session as non-strict xfail).
+csrc/pna.cu is checked by CPU emulation (tests/test_cpu_emulation_pna.py); GPU parity (kernel vs oracle, PNANet vs the
+reference fixture): tests/test_gpu_pna.py, green on the B200.
 """
 from __future__ import annotations
 

@@ -27,3 +27,21 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """Which branch of helpers.assert_parity decided each comparison: 'direct' = within tol of the fp32 oracle,
+    'arbiter' = not, but no farther from the fp64 oracle than 4x the fp32 oracle itself is, 'family' = no farther
+    from the fp64 oracle than the fp32 oracle's worst tensor of the same model (helpers.assert_grads_parity)."""
+    try:
+        from helpers import parity_summary
+    except Exception:
+        return
+    n, worst = parity_summary()
+    if sum(n.values()) == 0:
+        return
+    terminalreporter.write_line(f"assert_parity: {n['direct']} direct, {n['arbiter']} by fp64 arbiter, {n['family']} by "
+                                f"family bound (deep-model gradients), {n['FAIL']} failed")
+    for what, tol, e32, e64, eref, branch in worst:
+        terminalreporter.write_line(f"  [{branch}] {what}: |cuda-oracle32| {e32:.2e} |cuda-exact| {e64:.2e} "
+                                    f"|oracle32-exact| {eref:.2e} (tol {tol:.0e})")

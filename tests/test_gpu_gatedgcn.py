@@ -1,8 +1,7 @@
 """GatedGCN predictor + PE baselines on the GPU against the reference's own output / gradients
 (tests/golden/dgl_gatedgcn_net.pt) and the CPU oracle.
 
-The CUDA side (csrc/gated.cu, signnet_basisnet_b200/gatedgcn_net.py) was written after the round's GPU budget was spent
-and has not run on a GPU yet, so these tests run last in the GPU session as non-strict xfail (XPASS = parity observed); the oracle side is pinned by
+Parity first observed on a B200 in round 2; these are plain gates now.  The oracle side is pinned by
 tests/test_oracle_vs_reference.py / tests/test_oracle_golden.py on the CPU."""
 import os
 import types
@@ -11,14 +10,36 @@ import pytest
 import torch
 
 import restate
-from helpers import assert_close_rel, assert_grads_close
+from helpers import (assert_close_rel, assert_grads_close, assert_grads_parity, assert_parity,  # noqa: F401
+                     fp32_noise_samples)
 from signnet_basisnet_b200.synth import Data, synth_batch
 
-# Written after round 1's last GPU visit.  The kernels involved are plain streaming kernels (no barriers, no tensor cores:
-# nothing that can hang), their source is emulated on the CPU and the module wiring is dry-run, so the tests are allowed
-# to run - LAST in the session (file name) and as non-strict xfail: XPASS = parity observed, XFAIL = needs work, never red.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet observed on a GPU (XPASS = parity holds)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
+TOL = 1e-5
+
+
+def _leaf64(sd):
+    """fp64 leaf copy of a fixture's state_dict (the arbiter of helpers.assert_parity is the oracle run in fp64)."""
+    out = {k: (v.detach().clone().double() if v.is_floating_point() else v.detach().clone()) for k, v in sd.items()}
+    for k, v in out.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    return out
+
+
+def _pe64(d, sd64, prm, masked=True):
+    sub = {k[len("sign_inv_net."):]: v for k, v in sd64.items() if k.startswith("sign_inv_net.")}
+    x = d.pos_enc.unsqueeze(-1).double()
+    if masked:
+        return restate.masked_gin_deepsigns(x, d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph, sub,
+                                            prm["sign_inv_layers"], prm["pos_enc_dim"]).squeeze(-1)
+    return restate.gin_deepsigns(x, d.edge_index[0], d.edge_index[1], sub, prm["sign_inv_layers"],
+                                 prm["pos_enc_dim"]).squeeze(-1)
+
+
+def _g64(sd64, want):
+    return {k: sd64[k].grad for k in want}
 
 
 class _G:
@@ -73,18 +94,33 @@ def test_gatedgcn_net_golden(golden_dir):
     assert set(net.state_dict()) == set(g["state_dict"])
     net.load_state_dict(g["state_dict"])
     G = _G(d)
+    dc, sd64 = d.to("cpu"), _leaf64(g["state_dict"])
+    ref64 = restate.gatedgcn_net(dc.x[:, 0], _pe64(dc, sd64, prm), dc.edge_attr.reshape(-1), dc.edge_index[0],
+                                 dc.edge_index[1], dc.num_nodes_per_graph, sd64, prm["L"], prm["readout"],
+                                 prm["edge_feat"], prm["pe_aggregate"])
+    (ref64 * g["w"].double()).sum().backward()
     pe = handle_lap(net, d.pos_enc, G, DEV)                                # 'sign_inv', train_ZINC_graph_regression.py:20-25
     out, g_ret = net(G, d.x[:, 0], pe, d.edge_attr.reshape(-1), None)
     assert g_ret is G and out.shape == g["out"].shape
-    assert_close_rel(out.detach().cpu(), g["out"], 2e-5, what="GatedGCNNet vs reference")
+    assert_parity(out, g["out"], ref64, TOL, what="GatedGCNNet vs reference")
     (out * g["w"].to(DEV)).sum().backward()
     got = {k: p.grad.cpu() for k, p in net.named_parameters() if p.grad is not None}
     assert set(got) == set(g["grads"])
-    assert_grads_close(got, g["grads"], 1e-4, "GatedGCNNet vs reference")
+    def run(sd_):
+        sub = {k[len("sign_inv_net."):]: v for k, v in sd_.items() if k.startswith("sign_inv_net.")}
+        pe_ = restate.masked_gin_deepsigns(dc.pos_enc.unsqueeze(-1), dc.edge_index[0], dc.edge_index[1],
+                                           dc.num_nodes_per_graph, sub, prm["sign_inv_layers"], prm["pos_enc_dim"]).squeeze(-1)
+        o = restate.gatedgcn_net(dc.x[:, 0], pe_, dc.edge_attr.reshape(-1), dc.edge_index[0], dc.edge_index[1],
+                                 dc.num_nodes_per_graph, sd_, prm["L"], prm["readout"], prm["edge_feat"], prm["pe_aggregate"])
+        (o * g["w"]).sum().backward()
+        return {k: sd_[k].grad for k in g["grads"]}
+
+    assert_grads_parity(got, g["grads"], _g64(sd64, g["grads"]), TOL, "GatedGCNNet vs reference",
+                        samples=fp32_noise_samples(run, g["state_dict"], 3))
     after = net.state_dict()
     for k, v in g["state_dict_after"].items():
         if "running_" in k and k.startswith("layers."):
-            torch.testing.assert_close(after[k].cpu(), v, rtol=1e-5, atol=1e-6)
+            assert_parity(after[k], v, sd64[k], TOL, what=k)
 
 
 @pytest.mark.parametrize("method", ["sign_flip", "abs_val", "canonical", "none"])

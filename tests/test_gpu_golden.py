@@ -4,8 +4,11 @@ import os
 import pytest
 import torch
 
-from helpers import assert_close_rel, assert_grads_close, rows_to_dense, slot_row_index
+import restate
+from helpers import (assert_close_rel, assert_grads_parity, assert_parity, rows_to_dense, slot_row_index)
 from signnet_basisnet_b200.synth import Data
+
+TOL = 1e-5   # BASELINE.json north_star; the reference's own fp32 output is the target, an fp64 run of the oracle the arbiter
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -13,6 +16,27 @@ DEV = "cuda"
 
 def _load(golden_dir, name):
     return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _leaf64(sd):
+    """fp64 leaf copy of a fixture's state_dict: the 'exact' arbiter of helpers.assert_parity is the oracle run in fp64."""
+    out = {k: (v.detach().clone().double() if v.is_floating_point() else v.detach().clone()) for k, v in sd.items()}
+    for k, v in out.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    return out
+
+
+def _g64(sd64, strip=""):
+    return {k[len(strip):] if strip else k: v.grad for k, v in sd64.items() if v.requires_grad and v.grad is not None}
+
+
+def _f64(d):
+    out = d.to("cpu")
+    for k, v in list(out.__dict__.items()):
+        if torch.is_tensor(v) and v.is_floating_point():
+            setattr(out, k, v.double())
+    return out
 
 
 def test_dense_list_evd_golden_bit_exact(golden_dir):
@@ -57,15 +81,21 @@ def test_signnetgnn_golden(golden_dir):
     for lyr in model.sign_net.rho.transformer_layers:
         lyr.slf_attn.attention.dropout.p = 0.0
     model.train()
+    sd64 = _leaf64(m["state_dict"])
+    ref64 = restate.sign_net_gnn(_f64(d), sd64, c["nl_signnet"], c["nl_gnn"])
+    ref64.abs().sum().backward()
     out = model(d.to(DEV))
-    assert_close_rel(out.cpu(), m["out"], 1e-5, what="SignNetGNN vs reference (train)")
+    assert_parity(out, m["out"], ref64, TOL, what="SignNetGNN vs reference (train)")
     out.abs().sum().backward()
     got = {k: p.grad.cpu() for k, p in model.named_parameters() if p.grad is not None}
-    assert_grads_close(got, m["grads"], 5e-5, "SignNetGNN vs reference")
+    g64 = {k: v for k, v in _g64(sd64).items() if k in m["grads"]}
+    assert_grads_parity(got, m["grads"], g64, TOL, "SignNetGNN vs reference")
     model.eval()
     with torch.no_grad():
         out_e = model(d.to(DEV))
-    assert_close_rel(out_e.cpu(), m["out_eval"], 2e-5, what="SignNetGNN vs reference (eval)")
+        sd_e64 = {k: (v.double() if v.is_floating_point() else v) for k, v in m["state_dict_after"].items()}
+        ref_e64 = restate.sign_net_gnn(_f64(d), sd_e64, c["nl_signnet"], c["nl_gnn"], training=False)
+    assert_parity(out_e, m["out_eval"], ref_e64, TOL, what="SignNetGNN vs reference (eval)")
 
 
 class _G:
@@ -90,15 +120,24 @@ def test_dgl_deepsigns_golden(golden_dir, name):
                                 sign_inv_activation="relu", device=DEV)).to(DEV).train()
     assert set(net.state_dict()) == set(m["state_dict"])
     net.load_state_dict(m["state_dict"])
+    sd64, dc = _leaf64(m["state_dict"]), d.to("cpu")
+    x64 = dc.pos_enc.unsqueeze(-1).double()
+    if name == "gin":
+        ref64 = restate.gin_deepsigns(x64, dc.edge_index[0], dc.edge_index[1], sd64, m["cfg"]["layers"], k)
+    else:
+        ref64 = restate.masked_gin_deepsigns(x64, dc.edge_index[0], dc.edge_index[1], dc.num_nodes_per_graph, sd64,
+                                             m["cfg"]["layers"], k)
+    (ref64 * m["w"].double()).sum().backward()
     out = net(_G(d), d.pos_enc.unsqueeze(-1))
     assert out.shape == m["out"].shape
-    assert_close_rel(out.cpu(), m["out"], 2e-5, what=f"{name} vs reference")
+    assert_parity(out, m["out"], ref64, TOL, what=f"{name} vs reference")
     (out * m["w"].to(DEV)).sum().backward()
     got = {k_: p.grad.cpu() for k_, p in net.named_parameters() if p.grad is not None}
-    assert_grads_close(got, m["grads"], 1e-4, f"{name} vs reference")
+    assert_grads_parity(got, m["grads"], {k_: v for k_, v in _g64(sd64).items() if k_ in m["grads"]}, TOL,
+                        f"{name} vs reference")
     for k_, v in m["state_dict_after"].items():
         if "running_" in k_:
-            assert_close_rel(net.state_dict()[k_].cpu(), v, 2e-5, what=k_)
+            assert_parity(net.state_dict()[k_], v, sd64[k_], TOL, what=k_)
         elif "num_batches" in k_:
             assert torch.equal(net.state_dict()[k_].cpu(), v), k_
 
@@ -113,14 +152,22 @@ def test_gin_net_golden(golden_dir):
     assert set(net.state_dict()) == set(g["state_dict"])
     net.load_state_dict(g["state_dict"])
     G = _G(d)
+    sd64, dc = _leaf64(g["state_dict"]), d.to("cpu")
+    sub = {k[len("sign_inv_net."):]: v for k, v in sd64.items() if k.startswith("sign_inv_net.")}
+    pe64 = restate.masked_gin_deepsigns(dc.pos_enc.unsqueeze(-1).double(), dc.edge_index[0], dc.edge_index[1],
+                                        dc.num_nodes_per_graph, sub, prm["sign_inv_layers"], prm["pos_enc_dim"]).squeeze(-1)
+    ref64 = restate.gin_net(dc.x[:, 0], pe64, dc.edge_index[0], dc.edge_index[1], dc.num_nodes_per_graph, sd64, prm["L"],
+                            prm["readout"])
+    (ref64 * g["w"].double()).sum().backward()
     pe = net.sign_inv_net(G, d.pos_enc.unsqueeze(-1)).squeeze(-1)       # handle_lap, train_ZINC_graph_regression.py:20-25
     out, g_ret = net(G, d.x[:, 0], pe, torch.ones(d.edge_index.shape[1], 1, device=DEV), None)
     assert g_ret is G and out.shape == g["out"].shape
-    assert_close_rel(out.cpu(), g["out"], 2e-5, what="GINNet vs reference")
+    assert_parity(out, g["out"], ref64, TOL, what="GINNet vs reference")
     (out * g["w"].to(DEV)).sum().backward()
     got = {k: p.grad.cpu() for k, p in net.named_parameters() if p.grad is not None}
     assert set(got) == set(g["grads"])
-    assert_grads_close(got, g["grads"], 1e-4, "GINNet vs reference")
+    assert_grads_parity(got, g["grads"], {k: v for k, v in _g64(sd64).items() if k in g["grads"]}, TOL,
+                        "GINNet vs reference")
 
 
 @pytest.mark.parametrize("name", ["phi", "rho"])
@@ -133,9 +180,13 @@ def test_eq_deepsets_golden(golden_dir, name):
     net = SignPlus(EqDeepSetsEncoder(c["cin"], c["hid"], c["cout"], c["L"], use_bn=True)).to(DEV).train()
     assert set(net.state_dict()) == set(m["state_dict"])
     net.load_state_dict(m["state_dict"])
+    sd64 = _leaf64({k[len("model."):]: v for k, v in m["state_dict"].items()})
+    ref64 = restate.sign_plus_deepsets(m["x"].double(), sd64, "", c["L"])
+    (ref64 * m["w"].double()).sum().backward()
     out = net(m["x"].to(DEV))
-    assert_close_rel(out.cpu(), m["out"], 2e-5, what=f"SignPlus(EqDeepSets) {name} vs reference")
+    assert_parity(out, m["out"], ref64, TOL, what=f"SignPlus(EqDeepSets) {name} vs reference")
     (out * m["w"].to(DEV)).sum().backward()
     got = {k: p.grad.cpu() for k, p in net.named_parameters() if p.grad is not None}
     assert set(got) == set(m["grads"])
-    assert_grads_close(got, m["grads"], 1e-4, f"SignPlus(EqDeepSets) {name} vs reference")
+    assert_grads_parity(got, m["grads"], {"model." + k: v for k, v in _g64(sd64).items()}, TOL,
+                        f"SignPlus(EqDeepSets) {name} vs reference")

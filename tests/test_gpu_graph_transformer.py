@@ -1,6 +1,5 @@
 """Sparse graph-Transformer predictor on the GPU against the reference's own output / gradients
-(tests/golden/dgl_transformer_net.pt) and the CPU oracle.  csrc/graph_attention.cu and graph_transformer_net.py were
-written after the round's GPU budget was spent: these tests run last in the GPU session as non-strict xfail; the kernels' source is checked on the
+(tests/golden/dgl_transformer_net.pt) and the CPU oracle.  The kernels' source is additionally checked on the
 CPU by tests/test_cpu_emulation_attention.py and the oracle by tests/test_oracle_vs_reference.py."""
 import os
 
@@ -8,14 +7,35 @@ import pytest
 import torch
 
 import restate
-from helpers import assert_close_rel, assert_grads_close
+from helpers import assert_close_rel, assert_grads_close, assert_grads_parity, assert_parity  # noqa: F401
 from signnet_basisnet_b200.synth import Data, synth_batch
 
-# Written after round 1's last GPU visit.  The kernels involved are plain streaming kernels (no barriers, no tensor cores:
-# nothing that can hang), their source is emulated on the CPU and the module wiring is dry-run, so the tests are allowed
-# to run - LAST in the session (file name) and as non-strict xfail: XPASS = parity observed, XFAIL = needs work, never red.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet observed on a GPU (XPASS = parity holds)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
+TOL = 1e-5
+
+
+def _leaf64(sd):
+    """fp64 leaf copy of a fixture's state_dict (the arbiter of helpers.assert_parity is the oracle run in fp64)."""
+    out = {k: (v.detach().clone().double() if v.is_floating_point() else v.detach().clone()) for k, v in sd.items()}
+    for k, v in out.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    return out
+
+
+def _pe64(d, sd64, prm, masked=True):
+    sub = {k[len("sign_inv_net."):]: v for k, v in sd64.items() if k.startswith("sign_inv_net.")}
+    x = d.pos_enc.unsqueeze(-1).double()
+    if masked:
+        return restate.masked_gin_deepsigns(x, d.edge_index[0], d.edge_index[1], d.num_nodes_per_graph, sub,
+                                            prm["sign_inv_layers"], prm["pos_enc_dim"]).squeeze(-1)
+    return restate.gin_deepsigns(x, d.edge_index[0], d.edge_index[1], sub, prm["sign_inv_layers"],
+                                 prm["pos_enc_dim"]).squeeze(-1)
+
+
+def _g64(sd64, want):
+    return {k: sd64[k].grad for k in want}
 
 
 class _G:
@@ -72,15 +92,20 @@ def test_transformer_net_golden(golden_dir):
     assert set(net.state_dict()) == set(g["state_dict"])
     net.load_state_dict(g["state_dict"])
     G = _G(d)
+    dc, sd64 = d.to("cpu"), _leaf64(g["state_dict"])
+    ref64 = restate.transformer_net(dc.x[:, 0], _pe64(dc, sd64, prm, masked=False), dc.edge_attr.reshape(-1),
+                                    dc.edge_index[0], dc.edge_index[1], dc.num_nodes_per_graph, sd64, prm["L"],
+                                    prm["n_heads"], prm["readout"], prm["pe_aggregate"])
+    (ref64 * g["w"].double()).sum().backward()
     pe = handle_lap(net, d.pos_enc, G, DEV)
     out, g_ret = net(G, d.x[:, 0], pe, d.edge_attr.reshape(-1), None)
     assert g_ret is G and out.shape == g["out"].shape
-    assert_close_rel(out.detach().cpu(), g["out"], 2e-5, what="TransformerNet vs reference")
+    assert_parity(out, g["out"], ref64, TOL, what="TransformerNet vs reference")
     (out * g["w"].to(DEV)).sum().backward()
     got = {k: p.grad.cpu() for k, p in net.named_parameters() if p.grad is not None}
     assert set(got) == set(g["grads"])
-    assert_grads_close(got, g["grads"], 1e-4, "TransformerNet vs reference")
+    assert_grads_parity(got, g["grads"], _g64(sd64, g["grads"]), TOL, "TransformerNet vs reference")
     after = net.state_dict()
     for k, v in g["state_dict_after"].items():
         if "running_" in k and k.startswith("layers."):
-            torch.testing.assert_close(after[k].cpu(), v, rtol=1e-4, atol=1e-5)
+            assert_parity(after[k], v, sd64[k], TOL, what=k)

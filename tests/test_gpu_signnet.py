@@ -37,6 +37,7 @@ def _grads(sd):
 
 
 @pytest.mark.parametrize("shape,B,flavour,nhid,nl", [("alchemy", 24, "alchemy", 64, 3), ("zinc", 16, "alchemy", 128, 2),
+                                                     ("alchemy", 128, "alchemy", 64, 8), ("zinc", 64, "zinc", 128, 8),
                                                      ("zinc", 12, "zinc", 95, 3), ("alchemy", 9, "zinc", 20, 4)])
 def test_phi_stack_forward_backward(shape, B, flavour, nhid, nl):
     from signnet_basisnet_b200.layout import GraphIndex, pad4

@@ -111,6 +111,29 @@ int sb_gin_agg(const float* x, float* out, const float* res, const float* dotx, 
                int32_t masked, int32_t S, int32_t ld, int32_t tile_rows, int32_t force_generic, void* stream);
 int sb_gin_agg_tile_rows(int32_t ld); /* rows per shared-memory tile of the TMA path (0 = generic path only) */
 
+/* ---- the whole phi stack behind two calls (csrc/phi_stack.cu) -------------------------------------------------------
+ * GNN3d.forward (Alchemy/sign_net/sign_net.py:28-44) for both sign passes: L x { sb_gin_agg -> sb_linear_fwd (+ column
+ * statistics) -> sb_bn_finalize -> sb_linear_fwd (BN + ReLU prologue, + statistics) -> sb_bn_finalize ->
+ * sb_affine_act_res }, and its backward, enqueued back to back on `stream` by host C++ instead of ~20 Python-driven
+ * calls per layer.  The tables are HOST arrays of device pointers / sizes (read during the call, not retained):
+ *   fwd layer_ptrs[L][25] = { X_in, A, H, Y, X_out,  W0, bn0.weight, bn0.bias, W1, b1|NULL, eps, bn.weight, bn.bias,
+ *                             bn0.running_mean, bn0.running_var, bn.running_mean, bn.running_var,
+ *                             st0|NULL, st1|NULL (fp64 [S,2,C], zeroed by the caller; NULL = eval mode),
+ *                             a0, c0, mr0, a1, c1, mr1 (outputs of sb_bn_finalize, kept for the backward) }
+ *   bwd layer_ptrs[L][23] = { X, A, H, Y, a0, c0, mr0, a1, c1, mr1,  W0, bn0.weight, W1, eps, bn.weight,
+ *                             dW0, dbn0.weight, dbn0.bias, dW1, db1|NULL, deps (fp64 scalar, zeroed by the caller),
+ *                             dbn.weight, dbn.bias }
+ *   dims[L][4]            = { d_in, h, d, ld_in }  (ld_in = 1 for the [S,R] input of the first layer)
+ *   slot_ptrs[2][10]      = { graph_ptr, unit_ptr, unit_desc, in_pack, out_pack, row_ptr, in_ptr, in_src, out_ptr,
+ *                             out_dst }; slot_ints[2][6] = { R, B, k, masked, tile_rows, generic }: row 0 = the layout
+ *                             for padded rows, row 1 = the layout used while ld_in % 4 != 0 (first layer)
+ *   scratch[8]            = { G (in: dL/dX_L, updated in place), dY, dH, dA, out0, stats fp64 [S,2,Cmax],
+ *                             coef fp64 [3,S,Cmax], sb_linear_wgrad workspace } */
+int sb_phi_stack_fwd(const int64_t* layer_ptrs, const int32_t* dims, int32_t L, const int64_t* slot_ptrs,
+                     const int64_t* slot_ints, int32_t S, int32_t training, float momentum, float bn_eps, void* stream);
+int sb_phi_stack_bwd(const int64_t* layer_ptrs, const int32_t* dims, int32_t L, const int64_t* slot_ptrs,
+                     const int64_t* slot_ints, const int64_t* scratch, int32_t S, int32_t training, void* stream);
+
 /* ---- K2: Linear with fused BatchNorm prologue / statistics epilogue ------------------------------------------------
  * y[g*R+r, n] (+)= sum_k f(x[g*R+r, k]) * W[n*w_rs + k*w_cs] + bias[n];  f: pro 0 none, 1 pa*x+pc, 2 relu(pa*x+pc)
  * with pa/pc [G, K]; optional relu on the output; stats[G,2,N] += column sum / sum of squares of the output (fp64).
@@ -123,8 +146,12 @@ int sb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t w_rs, int
  * wgrad_tc.cu otherwise); 2: the same with the register-fed wgrad_tc.cu for every weight gradient (A/B switch of the
  * tests); 0: fp32 FFMA everywhere.  Returns the previous setting (-1 = not yet decided; env SB_DISABLE_TC=1 = 0). */
 int sb_set_tensor_cores(int32_t enable);
-/* Which kernel the last block launch of sb_linear_fwd used: 0 FFMA, 1 tcgen05, -1 none yet (the rank-1 / row-dot
- * streaming kernels do not update it).  Diagnostics for the tests. */
+/* 1 (default): problems with <= 8 192 rows (all groups) run on the small-row FFMA kernel (32-row tiles, both operands
+ * streamed; the predictor / rho contractions); 0: they take the tcgen05 / 128-row kernels like everything else (A/B
+ * switch of the tests).  Returns the previous setting. */
+int sb_set_small_rows(int32_t enable);
+/* Which kernel the last block launch of sb_linear_fwd used: 0 FFMA (128-row tiles), 1 tcgen05, 4 FFMA small-row,
+ * -1 none yet (the rank-1 / row-dot streaming kernels do not update it).  Diagnostics for the tests. */
 int sb_last_linear_kernel(void);
 /* Same for the last block launch of sb_linear_wgrad: 0 FFMA, 1 tcgen05 register-fed (wgrad_tc.cu), 3 tcgen05 TMA-fed
  * (wgrad_tc_tma.cu). */

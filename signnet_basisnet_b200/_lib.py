@@ -27,6 +27,8 @@ _SIGNATURES = {
     "sb_agg_unit_desc": "ppppp" + "iiii" + "pl" + "p",
     "sb_pack_neighbours": "pppp" + "l" + "p" + "p",
     "sb_gin_agg": "ppppp" + "p" + "ppppppp" + "l" + "iiiiiii" + "p",
+    "sb_phi_stack_fwd": "ppipp" + "ii" + "ff" + "p",
+    "sb_phi_stack_bwd": "ppippp" + "ii" + "p",
     "sb_linear_fwd": "pl" + "pll" + "p" + "pl" + "l" + "iii" + "ipp" + "i" + "p" + "i" + "p",
     "sb_linear_wgrad": "pl" + "pl" + "l" + "iii" + "ipp" + "pll" + "p" + "i" + "p" + "p",
     "sb_col_stats": "pll" + "ii" + "p" + "p",
@@ -86,6 +88,8 @@ def lib():
         L.sb_linear_wgrad_workspace_floats.restype = ctypes.c_int64
         L.sb_set_tensor_cores.restype = ctypes.c_int
         L.sb_set_tensor_cores.argtypes = [ctypes.c_int32]
+        L.sb_set_small_rows.restype = ctypes.c_int
+        L.sb_set_small_rows.argtypes = [ctypes.c_int32]
         L.sb_last_linear_kernel.restype = ctypes.c_int
         L.sb_last_wgrad_kernel.restype = ctypes.c_int
         L.sb_embedding_bwd_workspace_floats.restype = ctypes.c_int64
@@ -101,7 +105,7 @@ def lib():
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["sb_last_error", "sb_abi_version", "sb_device_sm_count", "sb_gin_agg_tile_rows",
                                        "sb_linear_wgrad_workspace_floats", "sb_embedding_bwd_workspace_floats",
-                                       "sb_set_tensor_cores", "sb_last_linear_kernel",
+                                       "sb_set_tensor_cores", "sb_set_small_rows", "sb_last_linear_kernel",
                                        "sb_last_wgrad_kernel"])
 
 
@@ -110,16 +114,26 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream   # (device index) -> cudaStream_t of torch's current stream
+
+
 def stream_ptr():
-    return torch.cuda.current_stream().cuda_stream
+    """cudaStream_t of torch's current stream on the current device.  (torch.cuda.current_stream().cuda_stream costs
+    ~15 us of Python per call - 5 ms per step at ~340 C-ABI calls, scripts/host_probe.py - the raw accessor < 1 us.)"""
+    return _raw_stream(torch._C._cuda_getDevice())
+
+
+_fn_cache: dict = {}
 
 
 def call(name, *args):
     """Invoke an entry point on torch's current stream; raises RuntimeError(sb_last_error()) on failure."""
-    L = lib()
-    rc = getattr(L, name)(*args, stream_ptr())
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(lib(), name)
+    rc = fn(*args, _raw_stream(torch._C._cuda_getDevice()))
     if rc != 0:
-        raise RuntimeError(f"{name} failed ({rc}): {L.sb_last_error().decode()}")
+        raise RuntimeError(f"{name} failed ({rc}): {lib().sb_last_error().decode()}")
 
 
 launch_count = 0  # number of C-ABI calls issued (each enqueues >= 1 kernel); bench.py reports it

@@ -18,6 +18,10 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def object_files():
+    return [os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o") for src in sources()]
+
+
 def _stale(obj, src):
     if not os.path.exists(obj):
         return True

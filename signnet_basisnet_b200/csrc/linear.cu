@@ -252,6 +252,129 @@ __global__ void __launch_bounds__(LIN_THREADS, (BN == 64) ? 2 : 1) linear_fwd_ke
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Small-row variant (same contract): the [N, d] contractions of the predictor / rho / the DGL MLPs have only a few
+// thousand rows; with 128-row tiles they fill 23 of the 148 SMs and every CTA first stages the whole weight
+// (51 us per launch at 2 922 rows, ncu launch list profiles/r2e_launches_b128.csv - 18 % of a 128-graph step).  Here a
+// CTA owns 32 rows x <= 128 columns and streams BOTH operands K-chunk by K-chunk through shared memory (the weight is
+// 64 KB and L2-resident), so a few-thousand-row problem spreads over ~100 CTAs and nothing waits for a 64 KB prologue.
+// Thread (tx = lane, ty = warp): rows 4 ty .. 4 ty + 3, columns tx, tx + 32, tx + 64, tx + 96 (conflict-free LDS, the
+// activation value is a warp-wide broadcast, every global store of a warp is one 128-byte line).
+#define LS_BM 32
+#define LS_BK 32
+#define LS_WP 129   // padded row of the weight chunk [LS_BK][128]
+
+__global__ void __launch_bounds__(256) linear_small_kernel(const LinArgs a) {
+  __shared__ float Xs[LS_BM][LS_BK + 1];
+  __shared__ float Ws[LS_BK][LS_WP];
+  __shared__ double sacc[2][128];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int K = a.K, N = a.N;
+  const long long tpg = (a.R + LS_BM - 1) / LS_BM;
+  const long long tile = blockIdx.x;
+  const int g = (int)(tile / tpg);
+  const long long row0 = (tile - (long long)g * tpg) * LS_BM;
+  const int rows = (int)((a.R - row0 < LS_BM) ? (a.R - row0) : LS_BM);
+  const long long base = (long long)g * a.R + row0;
+  if (a.stats) sacc[tid >> 7][tid & 127] = 0.0;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += LS_BK) {
+    // activation chunk [32 rows][32 k] with the prologue applied once per element
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = tid + 256 * q, r = idx >> 5, kk = idx & 31, k = k0 + kk;
+      float v = 0.f;
+      if (r < rows && k < K) {
+        v = __ldg(a.x + (base + r) * a.ldx + k);
+        if (a.pro) {
+          v = fmaf(__ldg(a.pa + (long long)g * K + k), v, __ldg(a.pc + (long long)g * K + k));
+          if (a.pro == 2) v = fmaxf(v, 0.f);
+        }
+      }
+      Xs[r][kk] = v;
+    }
+    // weight chunk Ws[kk][n] = W[n, k0 + kk]; the global index runs along the contiguous dimension of W
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int idx = tid + 256 * q;
+      int n, kk;
+      if (a.w_cs == 1) { kk = idx & 31; n = idx >> 5; } else { n = idx & 127; kk = idx >> 7; }
+      const int k = k0 + kk;
+      float v = 0.f;
+      if (n < N && k < K) v = __ldg(a.w + (long long)n * a.w_rs + (long long)k * a.w_cs);
+      Ws[kk][n] = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < LS_BK; ++kk) {
+      float xv[4], wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i] = Xs[ty * 4 + i][kk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv[j] = Ws[kk][tx + 32 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  double ssum[4] = {0.0, 0.0, 0.0, 0.0}, ssq[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty * 4 + i;
+    if (r >= rows) continue;
+    float* yrow = a.y + (base + r) * a.ldy;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = tx + 32 * j;
+      float t = acc[i][j];
+      if (col < N) {
+        if (a.bias) t += __ldg(a.bias + col);
+        if (a.accumulate) t += yrow[col];
+        if (a.relu) t = fmaxf(t, 0.f);
+        ssum[j] += (double)t;
+        ssq[j] += (double)t * (double)t;
+        yrow[col] = t;
+      } else if (col < a.ycols) {
+        yrow[col] = 0.f;
+      }
+    }
+  }
+  if (a.stats) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = tx + 32 * j;
+      if (col < N) {
+        atomicAdd(&sacc[0][col], ssum[j]);
+        atomicAdd(&sacc[1][col], ssq[j]);
+      }
+    }
+    __syncthreads();
+    const int col = tid & 127, which = tid >> 7;
+    if (col < N && sacc[which][col] != 0.0)
+      atomicAdd(a.stats + (long long)(g * 2 + which) * N + col, sacc[which][col]);
+  }
+}
+
+// rows (all groups) at or below which the small-row kernel is used instead of the tcgen05 / 128-row FFMA kernels
+#define LS_MAX_ROWS 8192
+
+static int launch_linear_small(const LinArgs& a, cudaStream_t st) {
+  const long long ntiles = sb_ceil_div(a.R, LS_BM) * a.G;
+  linear_small_kernel<<<(unsigned)ntiles, 256, 0, st>>>(a);
+  SB_CHECK_LAUNCH("sb_linear_fwd(small rows)");
+  return SB_OK;
+}
+
 static size_t lin_smem_bytes(int KP, int BN) {
   return ((size_t)KP * BN + 2 * LIN_BM * LIN_BKP) * sizeof(float) + (size_t)LIN_MAXG * 2 * BN * sizeof(double);
 }
@@ -268,7 +391,13 @@ int sb_linear_tc_launch(const float* x, int64_t ldx, const float* w, int64_t w_r
 // phi size); the CTA-pair, TMA-fed and weight-in-tensor-memory Linear variants were all slower than linear_tc.cu
 // (393 / 310 / 314 vs 292 us) and have been removed.
 static int g_use_tc = -1;
+static int g_small_rows = 1;   // SB_LINEAR_SMALL=0 / sb_set_small_rows(0): problems with few rows take the big-tile kernels
 static int g_last_variant = -1, g_last_wgrad_variant = -1;
+extern "C" int sb_set_small_rows(int32_t enable) {
+  const int old = g_small_rows;
+  g_small_rows = enable ? 1 : 0;
+  return old;
+}
 extern "C" int sb_last_linear_kernel(void) { return g_last_variant; }
 extern "C" int sb_last_wgrad_kernel(void) { return g_last_wgrad_variant; }
 extern "C" int sb_set_tensor_cores(int32_t enable) {
@@ -358,6 +487,12 @@ extern "C" int sb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_
       a.ycols = last_n ? (int)((ldy - n0 < 128) ? (ldy - n0) : 128) : 128;
       int rc = SB_ERR_UNSUPPORTED;
       int variant = 0;
+      if (g_small_rows && a.R * a.G <= LS_MAX_ROWS) {
+        rc = launch_linear_small(a, st);
+        if (rc != SB_OK) return rc;
+        g_last_variant = 4;
+        continue;
+      }
       if (use_tc()) {
         variant = 1;
         rc = sb_linear_tc_launch(a.x, a.ldx, a.w, a.w_rs, a.w_cs, a.bias, a.y, a.ldy, a.R, a.G, a.K, a.N, a.pro, a.pa,

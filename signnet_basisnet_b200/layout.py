@@ -71,6 +71,22 @@ class GraphIndex:
         self._checked = False
         self._slots = {}
 
+    def tensors(self):
+        out = [v for v in self.__dict__.values() if torch.is_tensor(v)]
+        for sl in self._slots.values():
+            out += [v for v in sl.__dict__.values() if torch.is_tensor(v)]
+        return out
+
+    def wait_ready(self):
+        """Make torch's current stream wait for the stream this index was built on (prepare_batch); no-op otherwise."""
+        ev = self.__dict__.get("ready")
+        if ev is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            for t in self.tensors():     # allocated on the builder's stream, consumed on this one
+                t.record_stream(cur)
+            self.ready = None
+
     def check(self, flags_host=None):
         """Raise ValueError for malformed inputs (mirrors the reference's implicit index errors)."""
         if self._checked:
@@ -141,3 +157,31 @@ class SlotLayout:
     @property
     def use_generic_agg(self) -> bool:
         return self.oversize > 0 or self.tile_rows <= 0
+
+
+def prepare_batch(data, ld: int = 128, stream=None, k=None, masked=True):
+    """Build the per-batch bookkeeping (GraphIndex + the slot-row layout for row stride `ld`) ahead of the step and
+    attach it to `data` (`data._b200_graph_index`, which the modules' forward(data) picks up).
+
+    With `stream` (a side stream on which `data`'s tensors are complete - e.g. the stream of the prefetching H2D copy)
+    the integer kernels AND the layout's one device->host read run there, one step ahead of the compute stream: the
+    host never waits for the previous step's backward in the middle of a step (at 128 graphs per GPU that wait made the
+    forward host-bound, scripts/host_probe.py).  The consumer calls GraphIndex.wait_ready() (done by the modules).
+    k=None selects the PyG trees' layout (k = N_max of the batch); otherwise the (k, masked) layout of the DGL trees."""
+    def build():
+        gi = GraphIndex(data.edge_index, data.batch, getattr(data, "num_graphs", None))
+        if k is None:
+            gi.slots_all(ld)
+        else:
+            gi.slots(k, masked, ld)
+        return gi
+
+    if stream is None:
+        gi = build()
+    else:
+        with torch.cuda.stream(stream):
+            gi = build()
+            gi.ready = torch.cuda.Event()
+            gi.ready.record(stream)
+    data._b200_graph_index = gi
+    return gi

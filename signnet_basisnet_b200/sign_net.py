@@ -156,21 +156,45 @@ class GNN3d(nn.Module):
         d = dims[-1][2]
         slots = gi.slots(k, masked, pad4(d))
         slots_in = gi.slots(k, masked, dims[0][0])
-        if self.training:  # two passes (+v, -v) through every BatchNorm (sign_net.py:113)
+        if self.training:  # one BatchNorm call per sign pass: two (+v, -v) under SignNet.forward (sign_net.py:113)
             for conv, norm in zip(self.convs, self.norms):
-                conv.nn.norms[0].bn.num_batches_tracked += 2
-                norm.bn.num_batches_tracked += 2
+                conv.nn.norms[0].bn.num_batches_tracked += int(x0.shape[0])
+                norm.bn.num_batches_tracked += int(x0.shape[0])
         cfg = dict(slots=slots, slots_in=slots_in, dims=dims, training=self.training, buffers=buffers,
                    capture=capture)
         return PhiStackFn.apply(x0, cfg, *params), slots
 
     def forward(self, x, edge_index, edge_attr=None, mask=None, batch=None, num_graphs=None):
-        """Reference signature GNN3d.forward(x[N,k,1], edge_index, edge_attr, mask[N,k]) (sign_net.py:28-44) for ONE
-        sign pass.  `batch` is additionally required (the reference reads graph membership implicitly from the mask).
-        Returns the padded dense view [N, k, n_out]."""
+        """Reference signature GNN3d.forward(x[N,k,n_in], edge_index, edge_attr, mask[N,k]) (sign_net.py:28-44): ONE
+        sign pass, returns the dense [N, k, n_out] tensor with zeros in the masked slots.  `batch` (graph id per node,
+        sorted) is additionally required: the reference reads graph membership implicitly from `mask`, the slot-row
+        layout needs it explicitly.  `mask`, when given, must be the reference's own mask (slot j valid iff j < n_b,
+        sign_net.py:100-102).  SignNet.forward does not come through here (it runs both sign passes side by side)."""
         if batch is None:
             raise ValueError("GNN3d.forward needs `batch` (graph id per node) on the B200 path")
-        raise NotImplementedError("single-sign GNN3d.forward: use SignNet.phi_pm / forward_rows (both signs at once)")
+        if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 3):
+            raise ValueError("x must be a CUDA float32 tensor [N, k, n_in] (no CPU fallback on the SignNet hot path)")
+        from .deepsigns import RowsToDenseFn
+
+        gi = GraphIndex(edge_index, batch, num_graphs)
+        N, k, C = x.shape
+        dims = self._flat_params()[0]
+        if C != dims[0][0] or N != gi.N:
+            raise ValueError(f"x is {tuple(x.shape)}; expected [{gi.N}, k, {dims[0][0]}]")
+        d = dims[-1][2]
+        masked = mask is not None
+        slots = gi.slots(k, masked, pad4(d))
+        if masked:
+            n = (gi.graph_ptr[1:] - gi.graph_ptr[:-1]).long()
+            want = torch.arange(k, device=x.device)[None, :] < n[gi.batch][:, None]
+            if mask.shape != want.shape or not torch.equal(mask.bool(), want):
+                raise ValueError("mask must be the SignNet slot mask: mask[i, j] = j < n_{batch[i]}")
+        ld = pad4(C) if C > 1 else 1
+        rows = torch.empty((1, slots.R) if ld == 1 else (1, slots.R, ld), dtype=torch.float32, device=x.device)
+        _call("sb_dense_to_rows", _p(x.contiguous()), slots.R, 1, 0, _p(gi.batch), _p(gi.graph_ptr), _p(slots.row_ptr),
+              gi.N, slots.k, int(slots.masked), C, ld, _p(rows))
+        xr, slots = self.forward_rows(rows, gi, k, masked)
+        return RowsToDenseFn.apply(xr, slots, d).view(N, k, d)
 
 
 def build_phi_input(gi: GraphIndex, slots, eigen_vectors=None, eigvecs_dense=None):
@@ -192,8 +216,8 @@ def build_phi_input(gi: GraphIndex, slots, eigen_vectors=None, eigvecs_dense=Non
 
 
 class SetTransformer(nn.Module):
-    """rho of the PyG trees (sign_net.py:46-72).  Round-1 scope: the nl_rho = 0 form (sum over slots -> Linear -> BN)
-    runs on the B200 kernels; the attention layers are SURVEY §8f rank 1 ("next")."""
+    """rho of the PyG trees (sign_net.py:46-72): nl_rho x TransformerEncoderLayer over the slot tokens of every node
+    (transformer.py: masked 4-head attention + FFN + MaskedLN on the B200 kernels), sum over slots, Linear -> BN."""
 
     def __init__(self, nhid, nlayer, flavour="alchemy"):
         super().__init__()
@@ -261,6 +285,7 @@ class SignNet(nn.Module):
         if edge_index is None:
             gi = graph_index or getattr(data, "_b200_graph_index", None) or GraphIndex(
                 data.edge_index, data.batch, getattr(data, "num_graphs", None))
+            gi.wait_ready()
             try:
                 data._b200_graph_index = gi
             except Exception:
@@ -321,6 +346,7 @@ class SignNetGNN(nn.Module):
         if edge_index is None:
             gi = getattr(data, "_b200_graph_index", None) or GraphIndex(data.edge_index, data.batch,
                                                                         getattr(data, "num_graphs", None))
+            gi.wait_ready()
             pos = self.sign_net(data, graph_index=gi)
             return self.gnn(data, pos, graph_index=gi)
         gi = GraphIndex(edge_index, batch, num_graphs)

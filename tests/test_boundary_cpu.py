@@ -87,6 +87,46 @@ def test_state_dict_keys_and_shapes_match_reference(flavour):
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_zinc_alias_has_the_reference_constructor_signatures():
+    """signnet_basisnet_b200.zinc mirrors GINESignNetPyG/core/sign_net.py:12,80,123 argument for argument (no extra
+    `flavour` kwarg): `from signnet_basisnet_b200.zinc import SignNetGNN` is a drop-in for train/zinc.py:60."""
+    import importlib
+    import inspect
+    import sys
+
+    from signnet_basisnet_b200 import zinc
+
+    sys.path.insert(0, os.path.join(ref_loader.REF_ROOT, "GINESignNetPyG"))
+    ref_loader.alchemy()
+    ref = importlib.import_module("core.sign_net")
+    for name in ("SignNetGNN", "SignNet", "GNN3d"):
+        want = list(inspect.signature(getattr(ref, name).__init__).parameters)
+        got = list(inspect.signature(getattr(zinc, name).__init__).parameters)
+        assert got == want, (name, got, want)
+    mine, theirs = zinc.SignNetGNN(None, None, 16, 1, 3, 2), ref.SignNetGNN(None, None, 16, 1, 3, 2)
+    assert set(mine.state_dict()) == set(theirs.state_dict())
+    mine.load_state_dict(theirs.state_dict())
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_gnn3d_forward_signature_matches_reference():
+    """GNN3d.forward(x, edge_index, edge_attr, mask) (sign_net.py:28): same leading arguments; `batch` is the one
+    documented addition."""
+    import inspect
+
+    from signnet_basisnet_b200.sign_net import GNN3d
+
+    want = list(inspect.signature(ref_loader.alchemy().GNN3d.forward).parameters)
+    got = list(inspect.signature(GNN3d.forward).parameters)
+    assert got[:len(want)] == want and got[len(want):] == ["batch", "num_graphs"], (got, want)
+    with pytest.raises(ValueError):
+        GNN3d(1, 8, 2)(torch.zeros(3, 2, 1), torch.zeros(2, 0, dtype=torch.long), None, None)      # no batch
+    with pytest.raises(ValueError):
+        GNN3d(1, 8, 2)(torch.zeros(3, 2, 1), torch.zeros(2, 0, dtype=torch.long), None, None,
+                       batch=torch.zeros(3, dtype=torch.long))                                     # CPU tensors
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
 def test_alchemy_config_parameter_count():
     """SURVEY §8c [probe]: SignNetGNN(6,4,n_hid=64,n_out=12,nl_signnet=8,nl_gnn=16) has 326 527 parameters."""
     from signnet_basisnet_b200.sign_net import SignNetGNN
@@ -183,7 +223,7 @@ def test_kernel_selection_switch_roundtrip():
         assert L.sb_set_tensor_cores(1) == 1
         L.sb_set_tensor_cores(-3)
         assert L.sb_set_tensor_cores(1) == 1
-        assert L.sb_last_linear_kernel() in (-1, 0, 1) and L.sb_last_wgrad_kernel() in (-1, 0, 1, 3)
+        assert L.sb_last_linear_kernel() in (-1, 0, 1, 4) and L.sb_last_wgrad_kernel() in (-1, 0, 1, 3)
     finally:
         L.sb_set_tensor_cores(1 if first < 0 else first)
 

@@ -51,9 +51,14 @@ def _worker(rank, world, port, out):
     live = [p for p in net.parameters()][:6]            # the last Linear never runs: its grads stay None
 
     def local_step(seed):
+        """-> this rank's own gradients of the step (taken with autograd.grad, which fires no accumulate hooks: once the
+        hooks are armed, a bucket's all-reduce may already be rewriting .grad in place when backward() returns)."""
         torch.manual_seed(seed + rank)
         x = torch.randn(4, 5)
+        own = torch.autograd.grad(net[3](net[2](net[1](net[0](x)))).sum(), live)
+        net[1].num_batches_tracked -= 1
         net[3](net[2](net[1](net[0](x)))).sum().backward()
+        return [g.clone() for g in own]
 
     def expected(local):
         mine = torch.cat([g.reshape(-1) for g in local])
@@ -63,8 +68,7 @@ def _worker(rank, world, port, out):
 
     res = {}
     # step 1 (discovery, un-overlapped), grads start as None
-    local_step(100)
-    want = expected([p.grad.clone() for p in live])
+    want = expected(local_step(100))
     sync.allreduce()
     got = torch.cat([p.grad.reshape(-1) for p in live])
     res["avg_ok_1"] = torch.allclose(got, want, atol=1e-7)
@@ -74,24 +78,20 @@ def _worker(rank, world, port, out):
     # step 2 (hooks launch the buckets during backward), grads reset to None
     for p in net.parameters():
         p.grad = None
-    local_step(200)
-    want = expected([p.grad.clone() for p in live])
+    want = expected(local_step(200))
     sync.allreduce()
     res["avg_ok_2"] = torch.allclose(torch.cat([p.grad.reshape(-1) for p in live]), want, atol=1e-7)
     # step 3: zero_grad(set_to_none=False) - autograd accumulates IN PLACE into the flat views (this used to
     # produce all-zero gradients)
     torch.optim.SGD(net.parameters(), lr=0.1).zero_grad(set_to_none=False)
     res["views_zeroed"] = bool((sync.flat == 0).all())
-    local_step(300)
-    want = expected([p.grad.clone() for p in live])
+    want = expected(local_step(300))
     sync.allreduce()
     got3 = torch.cat([p.grad.reshape(-1) for p in live])
     res["avg_ok_3"] = torch.allclose(got3, want, atol=1e-7) and bool(got3.abs().sum() > 0)
     # step 4: no zeroing at all (gradient accumulation): result = previous average + average of the new gradients
     prev = got3.clone()
-    before = [p.grad.clone() for p in live]
-    local_step(400)
-    want_new = expected([p.grad - b for p, b in zip(live, before)])
+    want_new = expected(local_step(400))
     sync.allreduce()
     res["accumulate_ok"] = torch.allclose(torch.cat([p.grad.reshape(-1) for p in live]), prev + want_new, atol=1e-6)
     if rank == 0:

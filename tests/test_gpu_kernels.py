@@ -161,6 +161,22 @@ def test_gin_aggregate_backward_mode(C, k, masked):
                                                (67, 4, 2, False, True), (200, 70, 0, True, True),
                                                (6, 130, 0, False, True)])
 def test_linear_fwd_and_stats(K, N, pro, relu, bias, R=333):
+    """Both kernel families behind sb_linear_fwd at this size: the small-row FFMA kernel (default up to 8 192 rows) and,
+    with sb_set_small_rows(0), the 128-row FFMA / tcgen05 kernels that larger problems take."""
+    from signnet_basisnet_b200 import _lib
+
+    L = _lib.lib()
+    for small in (1, 0):
+        old = L.sb_set_small_rows(small)
+        try:
+            _linear_fwd_and_stats(K, N, pro, relu, bias, R)
+            if K > 1 and N > 1:
+                assert (L.sb_last_linear_kernel() == 4) == bool(small), (small, L.sb_last_linear_kernel())
+        finally:
+            L.sb_set_small_rows(old)
+
+
+def _linear_fwd_and_stats(K, N, pro, relu, bias, R):
     from signnet_basisnet_b200.functional import linear_fwd
     from signnet_basisnet_b200.layout import pad4
 

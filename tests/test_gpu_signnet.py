@@ -168,3 +168,40 @@ def test_signnet_rho0_module(shape, B, ignore_eigval):
     o1 = net(dd)
     o2 = net2(None, dd.edge_index, eigV.to(DEV), dd.batch, None, eigS.to(DEV))
     assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("masked", [True, False])
+def test_gnn3d_forward_single_sign_pass(masked):
+    """The reference's own call GNN3d.forward(x[N,k,1], edge_index, edge_attr, mask[N,k]) (sign_net.py:28-44): ONE sign
+    pass, dense [N,k,d] result with zeros in the masked slots, one BatchNorm update - vs restate.gnn3d, fwd + grads."""
+    from signnet_basisnet_b200.sign_net import GNN3d
+
+    torch.manual_seed(5)
+    d = synth_batch(14, "alchemy", seed=17)
+    nhid, nl = 32, 3
+    phi = GNN3d(1, nhid, nl).to(DEV).train()
+    _, eigV = restate.dense_list_evd(d.eigen_values, d.eigen_vectors, d.batch)
+    k = eigV.shape[1] if masked else 4
+    eigV = eigV[:, :k].contiguous()
+    mask = restate.slot_mask(d.batch, k) if masked else None
+    sd, sd64 = _cpu_sd(phi), _cpu_sd(phi, dtype=torch.float64)
+    w = torch.randn(eigV.shape[0], k, nhid, generator=torch.Generator().manual_seed(6))
+    if masked:
+        w = w * mask.unsqueeze(-1)
+    ref = restate.gnn3d(eigV.unsqueeze(-1), d.edge_index, mask, sd, "", nl, True)
+    (ref * w).sum().backward()
+    ref64 = restate.gnn3d(eigV.double().unsqueeze(-1), d.edge_index, mask, sd64, "", nl, True)
+    (ref64 * w.double()).sum().backward()
+    out = phi(eigV.unsqueeze(-1).to(DEV), d.edge_index.to(DEV), None, None if mask is None else mask.to(DEV),
+              batch=d.batch.to(DEV))
+    assert out.shape == ref.shape
+    assert_parity(out, ref, ref64, TOL, what="GNN3d.forward")
+    if masked:
+        assert float(out[~mask.to(DEV)].abs().max()) == 0.0
+    (out * w.to(DEV)).sum().backward()
+    assert_grads_parity({n_: p.grad.cpu() for n_, p in phi.named_parameters() if p.grad is not None},
+                        _grads(sd), _grads(sd64), TOL, "GNN3d.forward")
+    _check_buffers(phi, sd, sd64, "GNN3d.forward")
+    if masked:
+        with pytest.raises(ValueError):
+            phi(eigV.unsqueeze(-1).to(DEV), d.edge_index.to(DEV), None, torch.ones_like(mask).to(DEV), batch=d.batch.to(DEV))

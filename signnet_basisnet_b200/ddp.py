@@ -16,6 +16,8 @@ path, not a port of anything.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -59,8 +61,11 @@ class FlatGradAllReduce:
     bucket is packed and all-reduced on a side stream the moment its last gradient has been accumulated.
     """
 
-    def __init__(self, module: torch.nn.Module, world: int | None = None, buckets: int = 4):
+    def __init__(self, module: torch.nn.Module, world: int | None = None, buckets: int = 4, overlap: bool | None = None):
         self.module = module
+        if overlap is None:
+            overlap = os.environ.get("SB_DDP_OVERLAP", "1") != "0"
+        self.overlap = bool(overlap)
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         self.n_buckets = max(1, int(buckets))
@@ -106,7 +111,7 @@ class FlatGradAllReduce:
             if b is None:
                 return                  # reported by allreduce(): a parameter thought dead received a gradient
             self._pending[b] -= 1
-            if self._pending[b] == 0 and self.world > 1:
+            if self._pending[b] == 0 and self.world > 1 and self.overlap:
                 self._launch(b)
         return hook
 
@@ -118,7 +123,7 @@ class FlatGradAllReduce:
         """Pack bucket b (gradients that are not already the flat views) and start its all-reduce."""
         lo, hi, idx = self._buckets[b]
         with torch.no_grad():
-            if self._side is not None:
+            if self._side is not None and self.overlap:
                 ev = torch.cuda.Event()
                 ev.record()                     # the backward stream: everything this bucket needs has been enqueued
                 ctx = torch.cuda.stream(self._side)

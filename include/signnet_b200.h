@@ -111,6 +111,21 @@ int sb_gin_agg(const float* x, float* out, const float* res, const float* dotx, 
                int32_t masked, int32_t S, int32_t ld, int32_t tile_rows, int32_t force_generic, void* stream);
 int sb_gin_agg_tile_rows(int32_t ld); /* rows per shared-memory tile of the TMA path (0 = generic path only) */
 
+/* ---- K1 + K2 fused (csrc/gin_lin_fused.cu): A = sb_gin_agg(X) and H = A W^T (+ fp64 column statistics of H, layout of
+ * sb_linear_fwd's `stats`) in one launch - MaskedGINConv.forward = GINConv aggregate then the first Linear of its
+ * MaskedMLP (Alchemy/sign_net/model_utils/masked_layers.py:74-84, :54-58).  The aggregated tile goes from shared memory
+ * straight into the tcgen05 contraction (weight resident in tensor memory); A is still written once because the
+ * backward's weight gradient reads it.  Fast path: ld = K = 128, h <= 128, S <= 2, TMA tile layout (tile_rows = 64, not
+ * `generic`).  Anything else returns SB_ERR_UNSUPPORTED (3) WITHOUT setting an error: run sb_gin_agg + sb_linear_fwd,
+ * which produce bit-identical A and H.  sb_set_fused_agg_linear(0/1) (env SB_FUSED_AGG_LINEAR) switches the fast path
+ * off/on and returns the previous setting (-1 = undecided). */
+int sb_gin_linear_fused_fwd(const float* x, float* a_out, float* h_out, double* stats, const float* eps, const float* w,
+                            int64_t w_rs, int64_t w_cs, int32_t K, int32_t h, int64_t ldh, const int32_t* unit_ptr,
+                            const int32_t* unit_desc, const uint32_t* nbr_pack, const int32_t* nbr_ptr,
+                            const int32_t* nbr_idx, int64_t R, int32_t B, int32_t S, int32_t ld, int32_t tile_rows,
+                            int32_t generic, void* stream);
+int sb_set_fused_agg_linear(int32_t enable);
+
 /* ---- the whole phi stack behind two calls (csrc/phi_stack.cu) -------------------------------------------------------
  * GNN3d.forward (Alchemy/sign_net/sign_net.py:28-44) for both sign passes: L x { sb_gin_agg -> sb_linear_fwd (+ column
  * statistics) -> sb_bn_finalize -> sb_linear_fwd (BN + ReLU prologue, + statistics) -> sb_bn_finalize ->

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "sb_agg_unit_desc": "ppppp" + "iiii" + "pl" + "p",
     "sb_pack_neighbours": "pppp" + "l" + "p" + "p",
     "sb_gin_agg": "ppppp" + "p" + "ppppppp" + "l" + "iiiiiii" + "p",
+    "sb_gin_linear_fused_fwd": "pppppp" + "ll" + "ii" + "l" + "ppppp" + "l" + "iiiii" + "p",
     "sb_phi_stack_fwd": "ppipp" + "ii" + "ff" + "p",
     "sb_phi_stack_bwd": "ppippp" + "ii" + "p",
     "sb_linear_fwd": "pl" + "pll" + "p" + "pl" + "l" + "iii" + "ipp" + "i" + "p" + "i" + "p",
@@ -88,6 +89,8 @@ def lib():
         L.sb_linear_wgrad_workspace_floats.restype = ctypes.c_int64
         L.sb_set_tensor_cores.restype = ctypes.c_int
         L.sb_set_tensor_cores.argtypes = [ctypes.c_int32]
+        L.sb_set_fused_agg_linear.restype = ctypes.c_int
+        L.sb_set_fused_agg_linear.argtypes = [ctypes.c_int32]
         L.sb_set_small_rows.restype = ctypes.c_int
         L.sb_set_small_rows.argtypes = [ctypes.c_int32]
         L.sb_last_linear_kernel.restype = ctypes.c_int
@@ -105,7 +108,7 @@ def lib():
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["sb_last_error", "sb_abi_version", "sb_device_sm_count", "sb_gin_agg_tile_rows",
                                        "sb_linear_wgrad_workspace_floats", "sb_embedding_bwd_workspace_floats",
-                                       "sb_set_tensor_cores", "sb_set_small_rows", "sb_last_linear_kernel",
+                                       "sb_set_tensor_cores", "sb_set_small_rows", "sb_set_fused_agg_linear", "sb_last_linear_kernel",
                                        "sb_last_wgrad_kernel"])
 
 

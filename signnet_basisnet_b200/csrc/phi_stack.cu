@@ -80,10 +80,17 @@ extern "C" int sb_phi_stack_fwd(const int64_t* layer_ptrs, const int32_t* dims, 
     const Slots& sl = (l == 0 && (ld_in % 4) != 0) ? in_sl : main_sl;
     const float* X = P<const float>(p[0]);
     float *A = P<float>(p[1]), *H = P<float>(p[2]), *Y = P<float>(p[3]), *Xn = P<float>(p[4]);
-    int rc = agg(sl, X, A, nullptr, nullptr, nullptr, P<const float>(p[10]), S, ld_in, false, stream);
-    if (rc) return rc;
-    rc = sb_linear_fwd(A, ld_in, P<const float>(p[5]), d_in, 1, nullptr, H, ldh, R, S, d_in, h, 0, nullptr, nullptr, 0,
-                       P<double>(p[17]), 0, stream);
+    // aggregate + first Linear: one fused launch where the shape allows it (gin_lin_fused.cu: A stays on the SM on its
+    // way into the contraction), else the two kernels - identical results either way
+    int rc = sb_gin_linear_fused_fwd(X, A, H, P<double>(p[17]), P<const float>(p[10]), P<const float>(p[5]), d_in, 1, d_in,
+                                     h, ldh, sl.unit_ptr, sl.unit_desc, sl.in_pack, sl.in_ptr, sl.in_src, sl.R, sl.B, S,
+                                     ld_in, sl.tile_rows, sl.generic, stream);
+    if (rc == SB_ERR_UNSUPPORTED) {
+      rc = agg(sl, X, A, nullptr, nullptr, nullptr, P<const float>(p[10]), S, ld_in, false, stream);
+      if (rc) return rc;
+      rc = sb_linear_fwd(A, ld_in, P<const float>(p[5]), d_in, 1, nullptr, H, ldh, R, S, d_in, h, 0, nullptr, nullptr, 0,
+                         P<double>(p[17]), 0, stream);
+    }
     if (rc) return rc;
     rc = sb_bn_finalize(P<const double>(p[17]), R, S, h, P<const float>(p[6]), P<const float>(p[7]), P<float>(p[13]),
                         P<float>(p[14]), momentum, bn_eps, training, P<float>(p[19]), P<float>(p[20]), P<double>(p[21]),

@@ -50,3 +50,4 @@ def test_wgrad_tma_matches_register_fed(R, pro, bias, G):
                          what="dbias")
         assert torch.equal(out[1][1], out[2][1])
     assert torch.equal(out[1][0], out[2][0])
+

@@ -274,33 +274,69 @@ def run_b200(args):
     kernels = [{"entry": k, "launches_per_step": c / args.steps, "ms_per_step": t / args.steps,
                 "share": t / total_prof} for k, (c, t) in sorted(prof.items(), key=lambda kv: -kv[1][1])][:12]
 
-    # roofline of the phi aggregate (K1): bytes = 2*4*ld*S*R + 16*E per launch, forward launches
+    # roofline of the phi aggregate (K1).  SURVEY §8d: bytes = 2*4*ld*S*R + 16*E per launch (read X, write A, read the
+    # int64 edge_index once).  In the default path the forward aggregate runs INSIDE gin_lin_fused_kernel, which also
+    # writes the first Linear's output H (one more activation tensor): its algorithmic bytes are 3*4*ld*S*R + 16*E.
+    # The stand-alone K1 kernel still runs in the backward (transposed CSR; dA, G, X in, G out = 4 tensors) and is also
+    # timed here on its own, live, with CUDA events on the launching stream.
     gi = prepare_batch(resident, LD)
     sl = gi.slots_all(CFG["n_hid"])
-    agg_bytes = 2 * 4 * CFG["n_hid"] * 2 * sl.R + 16 * gi.E
+    ld, T1 = CFG["n_hid"], 4 * CFG["n_hid"] * 2 * sl.R
     peak, peak_src = peaks()
-    roof = None
-    tag = f"sb_gin_agg[ld={CFG['n_hid']}]"
-    if tag in prof:
+    traffic = traffic_src = None
+    tp = os.path.join(ROOT, "profiles", "agg_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic_src = "static: " + tj.get("source", "ncu --set full capture of an earlier run (profiles/)")
+
+    def rec(tag, nbytes):
+        if tag not in prof:
+            return None
         c, t = prof[tag]
-        ach = agg_bytes / (t / c * 1e-3) / 1e9
-        traffic = traffic_src = None
-        tp = os.path.join(ROOT, "profiles", "agg_traffic.json")
-        if os.path.exists(tp):
-            tj = json.load(open(tp))
-            traffic = tj.get("dram_bytes_per_launch")
-            traffic_src = "static: " + tj.get("source", "ncu --set full capture of an earlier run (profiles/)")
-        roof = {"kernel": "gin_agg_tma_kernel (phi aggregate, forward)", "bound": "hbm", "achieved": round(ach, 1),
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": agg_bytes,
-                "avg_launch_us": round(t / c * 1e3, 1), "launches_per_step": c / args.steps,
-                "slot_rows_R": sl.R, "dense_slot_bytes_per_launch": 2 * 4 * CFG["n_hid"] * 2 * gi.N * sl.k + 16 * gi.E}
-        btag = f"sb_gin_agg[ld={CFG['n_hid']},bwd]"
-        if btag in prof:
-            cb, tb = prof[btag]
-            bb = 4 * 4 * CFG["n_hid"] * 2 * sl.R + 16 * gi.E  # dA, G, X in; G out
-            roof["backward"] = {"achieved": round(bb / (tb / cb * 1e-3) / 1e9, 1), "bytes_per_launch": bb,
-                                "avg_launch_us": round(tb / cb * 1e3, 1)}
+        ach = nbytes / (t / c * 1e-3) / 1e9
+        return {"achieved": round(ach, 1), "frac": round(ach / peak, 4), "bytes_per_launch": nbytes,
+                "avg_launch_us": round(t / c * 1e3, 1), "launches_per_step": c / args.steps}
+
+    from signnet_basisnet_b200.phi import gin_agg
+
+    xs = torch.randn(2, sl.R, ld, device=dev)
+    ys = torch.empty_like(xs)
+    for _ in range(3):
+        gin_agg(xs, ys, sl, 2, ld)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(7):
+        gin_agg(xs, ys, sl, 2, ld)
+    ev1.record()
+    torch.cuda.synchronize()
+    t_alone = ev0.elapsed_time(ev1) / 7
+    alone_bytes = 2 * T1 + 16 * gi.E
+    alone = {"kernel": "gin_agg_tma_kernel (K1 alone, forward CSR), 7 launches timed live outside the step",
+             "achieved": round(alone_bytes / (t_alone * 1e-3) / 1e9, 1), "bytes_per_launch": alone_bytes,
+             "frac": round(alone_bytes / (t_alone * 1e-3) / 1e9 / peak, 4), "avg_launch_us": round(t_alone * 1e3, 1),
+             "traffic": (tj.get("dram_bytes_per_launch") if traffic_src else None), "traffic_source": traffic_src}
+    del xs, ys
+    fused = rec("sb_gin_linear_fused_fwd", 3 * T1 + 16 * gi.E)
+    fwd = rec(f"sb_gin_agg[ld={ld}]", alone_bytes)
+    bwd = rec(f"sb_gin_agg[ld={ld},bwd]", 4 * T1 + 16 * gi.E)
+    main = fused or fwd
+    roof = None
+    if main is not None:
+        roof = {"kernel": ("gin_lin_fused_kernel (phi aggregate K1 + first Linear of the MaskedMLP, forward; csrc/gin_lin_fused.cu)"
+                           if fused else "gin_agg_tma_kernel (phi aggregate, forward)"),
+                "bound": "hbm", "achieved": main["achieved"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": main["frac"], "traffic": None if fused else alone["traffic"],
+                "traffic_source": None if fused else traffic_src,
+                "algorithmic_bytes_per_launch": main["bytes_per_launch"],
+                "algorithmic_bytes_note": ("X read + A written + H written (3 activation tensors) + int64 edge_index once; "
+                                           "K1 alone is 2 tensors (SURVEY §8d)" if fused else "SURVEY §8d"),
+                "avg_launch_us": main["avg_launch_us"], "launches_per_step": main["launches_per_step"],
+                "slot_rows_R": sl.R, "dense_slot_bytes_per_launch": 2 * 4 * ld * 2 * gi.N * sl.k + 16 * gi.E,
+                "aggregate_alone": alone, "backward": bwd}
+        fp = os.path.join(ROOT, "profiles", "fused_traffic.json")
+        if fused and os.path.exists(fp):
+            fj = json.load(open(fp))
+            roof["traffic"], roof["traffic_source"] = fj.get("dram_bytes_per_launch"), "static: " + fj.get("source", "")
 
     if rank != 0:
         if world > 1:

@@ -139,6 +139,28 @@ def call(name, *args):
         raise RuntimeError(f"{name} failed ({rc}): {lib().sb_last_error().decode()}")
 
 
+def try_call(name, *args):
+    """Like counted_call for entry points that may answer SB_ERR_UNSUPPORTED (3) without an error: returns True if the
+    call ran, False if the caller must take its fallback; any other non-zero code raises."""
+    global launch_count
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(lib(), name)
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = fn(*args, _raw_stream(torch._C._cuda_getDevice()))
+    if rc == 3:
+        return False
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib().sb_last_error().decode()}")
+    launch_count += 1
+    if _profile is not None:
+        e1.record()
+        _profile.append((_profile_tag(name, args), e0, e1))
+    return True
+
+
 launch_count = 0  # number of C-ABI calls issued (each enqueues >= 1 kernel); bench.py reports it
 _profile = None   # None = off; else list of (tag, start_event, end_event) on torch's current stream
 

@@ -224,10 +224,14 @@ class _PhiStackPerCallFn:
             sl = cfg["slots_in"] if (l == 0 and ld_in % 4 != 0) else slots
             A = torch.empty(S, R, ld_in, dtype=torch.float32, device=dev) if ld_in > 1 else torch.empty(
                 S, R, dtype=torch.float32, device=dev)
-            gin_agg(X, A, sl, S, ld_in, eps=eps)
             st0 = torch.zeros(S, 2, h, dtype=torch.float64, device=dev) if training else None
             H = torch.empty(S, R, ldh, dtype=torch.float32, device=dev)
-            linear_fwd(A, ld_in, W0, d_in, 1, None, H, ldh, R, S, d_in, h, stats=st0)
+            gi = sl.gi   # aggregate + first Linear: the fused kernel where the shape allows it, else the two kernels
+            if not _lib.try_call("sb_gin_linear_fused_fwd", _p(X), _p(A), _p(H), _p(st0), _p(eps), _p(W0), d_in, 1, d_in, h,
+                                 ldh, _p(sl.unit_ptr), _p(sl.unit_desc), _p(gi.in_pack), _p(gi.in_ptr), _p(gi.in_src),
+                                 sl.R, gi.B, S, ld_in, max(sl.tile_rows, 1), int(sl.use_generic_agg or ld_in % 4 != 0)):
+                gin_agg(X, A, sl, S, ld_in, eps=eps)
+                linear_fwd(A, ld_in, W0, d_in, 1, None, H, ldh, R, S, d_in, h, stats=st0)
             a0, c0, mr0 = bn_finalize(st0, R, S, h, g0, b0, rm0, rv0, training, dev)
             st1 = torch.zeros(S, 2, d, dtype=torch.float64, device=dev) if training else None
             Y = torch.empty(S, R, ldd, dtype=torch.float32, device=dev)

@@ -270,7 +270,9 @@ int sb_segment_pool_fwd(const float* x, int64_t ldx, const int32_t* graph_ptr, i
                         float* out, int64_t ldo, void* stream);
 int sb_segment_pool_bwd(const float* gout, int64_t ldo, const int64_t* batch, const int32_t* graph_ptr, int64_t N,
                         int32_t C, int32_t mean, float* gx, int64_t ldx, void* stream);
-/* DiscreteEncoder (elements.py:21-37), one integer feature column per call; flags bit 0 = index out of range */
+/* DiscreteEncoder (elements.py:21-37), one integer feature column per call.  An index outside [0, V) sets flags bit 0
+ * (if flags != NULL), prints the offending row and TRAPS (the CUDA counterpart of nn.Embedding's IndexError: a
+ * device-side assert; the next CUDA call of the process fails). */
 int sb_embedding_fwd(const int64_t* idx, int64_t stride, const float* table, int32_t V, int32_t C, int64_t M,
                      float* out, int64_t ldo, int32_t accumulate, int32_t* flags, void* stream);
 int sb_embedding_bwd(const int64_t* idx, int64_t stride, const float* g, int64_t ldg, int32_t V, int32_t C, int64_t M,

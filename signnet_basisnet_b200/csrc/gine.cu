@@ -199,7 +199,14 @@ __global__ void embedding_fwd_kernel(const int64_t* __restrict__ idx, long long 
     const long long v = idx[m * stride];
     float val = 0.f;
     if (v < 0 || v >= V) {
-      if (c == 0) atomicOr(flags, 1);
+      // nn.Embedding raises for such an index (CPU: IndexError; CUDA: device-side assert).  Same here: the flag is
+      // set for callers that read it, and the kernel traps - the next CUDA call of the process reports the failure
+      // instead of training silently on zero embeddings.
+      if (c == 0) {
+        if (flags) atomicOr(flags, 1);
+        printf("libsignnet_b200: DiscreteEncoder index %lld out of range [0, %d) at row %lld\n", v, V, m);
+      }
+      __trap();
     } else if (c < C) {
       val = __ldg(table + v * C + c);
     }

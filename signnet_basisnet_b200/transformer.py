@@ -6,8 +6,10 @@ state_dict keys.  Tokens are the valid slot rows of a node, so all `x[~mask] = 0
 
 Reference quirk kept: MultiHeadAttention builds ScaledDotProductAttention with its default attn_dropout = 0.1
 (transformer_module.py:46,85), i.e. attention probabilities are dropped in training mode even though every other
-dropout of the model is 0.  `attn_dropout` reproduces it with a counter-based generator (not torch's RNG stream, so
-training-mode parity is checked with the dropout set to 0, cf. oracle/restate.py:set_transformer).
+dropout of the model is 0.  It is reproduced with a counter-based generator inside the kernels, seeded per layer call
+from torch's CPU generator (not torch's CUDA Philox stream: the masks differ from the reference's element for element, so
+training-mode parity is checked with the dropout set to 0, cf. oracle/restate.py:set_transformer; the statistics - keep
+probability, 1/(1-p) scaling, fresh mask per layer and step, same mask in forward and backward - are tested).
 """
 from __future__ import annotations
 
@@ -123,7 +125,13 @@ class MultiHeadAttention(nn.Module):
         v = linear(x_rows, self.w_vs.weight, None, hd)
         p = self.attention.dropout.p if self.training else 0.0
         self._calls += 1
-        seed = (torch.initial_seed() + 0x5851F42D * self._calls) & 0x7FFFFFFFFFFFFFFF
+        seed = 0
+        if p > 0.0:
+            # one draw per layer call from torch's CPU generator: independent masks per layer, per step and - when the
+            # ranks are seeded differently, as DDP scripts do - per rank; reproducible under torch.manual_seed and
+            # resumable with torch.get_rng_state() (the seed used to be a function of the call count alone,
+            # so all rho layers of a step dropped the same attention entries)
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         o = AttentionFn.apply(q, k, v, slots, self.n_head, self.d_k, p, seed)
         o = linear(o, self.fc.weight, None, pad4(self.d_model))
         return self.norm(o, x_rows)

@@ -139,3 +139,63 @@ def test_attention_dropout_is_reproducible_in_backward():
     rhs = (gv * dv).sum()
     torch.testing.assert_close(lhs, rhs, rtol=1e-4, atol=1e-4)
     assert not torch.equal(o, AttentionFn.apply(q, k, v, sl, 4, 8, 0.0, 1234))
+
+
+def test_attention_dropout_statistics_and_per_layer_seeds():
+    """The reference's quirk (attention dropout p = 0.1 in training mode, transformer_module.py:46,56-57) is reproduced
+    with the kernels' own counter-based generator, so masks cannot match torch's element for element; what must hold:
+    every attention probability is kept with probability 1 - p and scaled by 1/(1 - p), the mask is a function of the
+    seed, and every layer call draws a NEW seed from torch's generator (all rho layers of a step used to
+    share one mask)."""
+    from helpers import slot_row_index
+    from signnet_basisnet_b200 import transformer as tr
+    from signnet_basisnet_b200.layout import GraphIndex
+
+    d = synth_batch(64, "alchemy", seed=34)
+    gi = GraphIndex(d.edge_index.to(DEV), d.batch.to(DEV), d.num_graphs)
+    sl = gi.slots_all(32)
+    idx = slot_row_index(d.batch, sl.k, True).to(DEV)                 # [N, k] -> row or -1
+    q = torch.zeros(sl.R, 32, device=DEV)                             # q = k = 0: uniform attention 1 / k_b
+    v = torch.zeros(sl.R, 32, device=DEV)
+    node, slot = torch.nonzero(idx >= 0, as_tuple=True)
+    v[idx[node, slot], slot] = 1.0                                    # token j carries the one-hot e_j: o = P itself
+    p = 0.1
+    o1 = tr.AttentionFn.apply(q, q, v, sl, 1, 32, p, 1111)
+    o2 = tr.AttentionFn.apply(q, q, v, sl, 1, 32, p, 2222)
+    assert torch.equal(o1, tr.AttentionFn.apply(q, q, v, sl, 1, 32, p, 1111)) and not torch.equal(o1, o2)
+    n = torch.bincount(d.batch).to(DEV)
+    kb = n[gi.batch][node].float()                                    # k_b of the row's graph (all slots valid: k = N_max)
+    rows = o1[idx[node, slot]]                                        # [R, 32]
+    valid = torch.arange(32, device=DEV)[None, :] < kb[:, None]
+    kept = rows[valid] != 0
+    want = (1.0 / (kb * (1 - p)))[:, None].expand(-1, 32)[valid]
+    torch.testing.assert_close(rows[valid][kept], want[kept], rtol=1e-5, atol=1e-7)
+    frac = float(kept.float().mean())
+    assert abs(frac - (1 - p)) < 0.01, frac
+    assert float(rows[~valid].abs().max()) == 0.0
+    # per-layer-call seeds come from torch's generator
+    seeds = []
+    real = tr.AttentionFn.apply
+
+    class Spy:
+        @staticmethod
+        def apply(q_, k_, v_, sl_, h_, dk_, p_, seed_):
+            seeds.append(seed_)
+            return real(q_, k_, v_, sl_, h_, dk_, p_, seed_)
+
+    torch.manual_seed(5)
+    layers = [tr.MultiHeadAttention(4, 32, 8, 8).to(DEV).train() for _ in range(3)]
+    x = torch.randn(sl.R, 32, device=DEV)
+    tr.AttentionFn = Spy
+    try:
+        for lyr in layers:
+            lyr(x, sl)
+        first = list(seeds)
+        torch.manual_seed(5)
+        [tr.MultiHeadAttention(4, 32, 8, 8) for _ in range(3)]       # same generator consumption as above
+        for lyr in layers:
+            lyr(x, sl)
+    finally:
+        tr.AttentionFn = real
+    assert len(set(first)) == 3, first                                # independent masks per layer
+    assert seeds[3:] == first                                         # reproducible under torch.manual_seed

@@ -208,7 +208,22 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    import gc
+
     def timed(fn, n):
+        # the cyclic collector is paused inside a timed region (a full collection of this process is a 10-20 ms pause
+        # that lands in one random step of a 20-step window); reference cycles wait until the region ends
+        gc.collect()
+        gc_was = gc.isenabled()
+        if os.environ.get("SB_BENCH_GC") != "1":
+            gc.disable()
+        try:
+            return _timed(fn, n)
+        finally:
+            if gc_was:
+                gc.enable()
+
+    def _timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -124,18 +124,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
   const int K = a.K, N = a.N;
 
   // ---- one-time: split the weight into head/tail, canonical K-major SW128 blocks; rows >= N and columns >= K are 0
-  for (int idx = tid; idx < nkb * 128 * TC_KB; idx += TC_THREADS) {
-    // lanes run along k for either weight orientation: one 128-byte swizzle row per warp store = conflict-free.  (With
-    // lanes along n - the coalesced order for the transposed weight of the input-gradient launches - all 32 stores of a
-    // warp hit the same bank: 32-way conflicts cost ~10 % of such a launch; the strided global reads are L2 hits.)
-    const int n = idx / (nkb * TC_KB), k = idx - n * (nkb * TC_KB);
-    float v = 0.f;
-    if (k < K && n < N) v = __ldg(a.w + (long long)n * a.w_rs + (long long)k * a.w_cs);
-    float h, l;
-    tc_split(v, h, l);
-    const uint32_t off = (uint32_t)(k / TC_KB) * TC_BLK_BYTES + tc_sw128(n, (k % TC_KB) >> 2) + (uint32_t)(k & 3) * 4;
-    *reinterpret_cast<float*>(Wh + off) = h;
-    *reinterpret_cast<float*>(Wl + off) = l;
+  // lanes run along k for either weight orientation: one 128-byte swizzle row per warp store = conflict-free.  (With
+  // lanes along n - the coalesced order for the transposed weight of the input-gradient launches - all 32 stores of a
+  // warp hit the same bank: 32-way conflicts cost ~10 % of such a launch; the strided global reads are L2 hits.)
+  // Six loads per thread are issued before their first use: the prologue is ~10 us of a 46 us launch at 139 k rows (one
+  // eighth of the phi size) when every load waits for the previous one's store.
+  {
+    constexpr int UN = 6;
+    const int total = nkb * 128 * TC_KB, rowlen = nkb * TC_KB;
+    for (int base0 = tid; base0 < total; base0 += TC_THREADS * UN) {
+      float v[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int idx = base0 + u * TC_THREADS;
+        const int n = idx / rowlen, k = idx - n * rowlen;
+        v[u] = (idx < total && k < K && n < N) ? __ldg(a.w + (long long)n * a.w_rs + (long long)k * a.w_cs) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int idx = base0 + u * TC_THREADS;
+        if (idx < total) {
+          const int n = idx / rowlen, k = idx - n * rowlen;
+          float h, l;
+          tc_split(v[u], h, l);
+          const uint32_t off = (uint32_t)(k / TC_KB) * TC_BLK_BYTES + tc_sw128(n, (k % TC_KB) >> 2) + (uint32_t)(k & 3) * 4;
+          *reinterpret_cast<float*>(Wh + off) = h;
+          *reinterpret_cast<float*>(Wl + off) = l;
+        }
+      }
+    }
   }
   for (int idx = tid; idx < TC_MAXG * 128; idx += TC_THREADS) {
     const int g = idx >> 7, c = idx & 127;

@@ -5,8 +5,8 @@
 // ([32 rows x 32 floats] boxes, SWIZZLE_128B_ATOM_32B = the MN-major tf32 layout the UMMA descriptor names
 // SWIZZLE_128B_BASE32B; rows past the end of a group are zero-filled) straight into the head buffers of a 3-stage ring,
 // up to three chunks (96 KB) ahead of the MMAs, and the 16 worker warps only add the 3xTF32 tails in place (plus the
-// rewritten heads: `rawhead` - letting the tensor core truncate the raw fp32 word itself - is measured 3 % faster but
-// not bit-identical to wgrad_tc.cu and stays off).
+// rewritten heads; letting the tensor core truncate the raw fp32 word itself was measured 3 % faster in round 2 but is
+// not bit-identical to wgrad_tc.cu and was dropped).
 //
 // STATUS (round 2, B200): bit-identical to wgrad_tc.cu on every case of scripts/pair_check.cu and tests/test_gpu_wgrad_
 // variants.py; 278 us vs 338 us per launch at the phi size of cfg 4 (profiles/r2a_pair_check_mode3.log).
@@ -36,7 +36,6 @@ struct WgTmaArgs {
   const float* pc;
   float* part_w;   // [grid][128][128]
   float* part_b;   // [grid][128] or null
-  int rawhead;
 };
 
 __device__ __forceinline__ uint64_t wm_make_desc(uint32_t saddr) {
@@ -67,9 +66,6 @@ __device__ __forceinline__ void wm_prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-__device__ __forceinline__ float wm_tail_trunc(float x) {   // x minus the tf32 the tensor core reads from the raw word
-  return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-}
 // 3-D tensor-map load (column, row inside the group, group) of one [32 rows x 32 floats] box
 __device__ __forceinline__ void wm_tma_load(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -175,7 +171,6 @@ wgrad_tc_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap tmg, 
     // item q of a thread: idx = tid + 512 q -> 32-feature block (idx >> 8), row (idx >> 3) & 31, float4 (idx & 7)
     float dbs[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     const int row = (tid >> 3) & 31, c4 = tid & 7;
-    const bool raw_g = a.rawhead != 0, raw_x = a.rawhead && !a.pro;
     unsigned cnt = 0;
     for (long long c = blockIdx.x; c < nch; c += gridDim.x, ++cnt) {
       const int stage = cnt % WM_STAGES;
@@ -194,18 +189,12 @@ wgrad_tc_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap tmg, 
         const float4 vg = *reinterpret_cast<const float4*>(sb + off);
         dbs[q][0] += vg.x; dbs[q][1] += vg.y; dbs[q][2] += vg.z; dbs[q][3] += vg.w;
         float4 h, l;
-        if (raw_g) {
-          l = make_float4(wm_tail_trunc(vg.x), wm_tail_trunc(vg.y), wm_tail_trunc(vg.z), wm_tail_trunc(vg.w));
-        } else {
-          wm_split(vg.x, h.x, l.x); wm_split(vg.y, h.y, l.y); wm_split(vg.z, h.z, l.z); wm_split(vg.w, h.w, l.w);
-          *reinterpret_cast<float4*>(sb + off) = h;
-        }
+        wm_split(vg.x, h.x, l.x); wm_split(vg.y, h.y, l.y); wm_split(vg.z, h.z, l.z); wm_split(vg.w, h.w, l.w);
+        *reinterpret_cast<float4*>(sb + off) = h;
         *reinterpret_cast<float4*>(sb + WM_BLK_BYTES + off) = l;
         // ---- x: the forward prologue (BatchNorm affine / ReLU) is recomputed, never stored
         const float4 vx = *reinterpret_cast<const float4*>(sb + 2 * WM_BLK_BYTES + off);
-        if (raw_x) {
-          l = make_float4(wm_tail_trunc(vx.x), wm_tail_trunc(vx.y), wm_tail_trunc(vx.z), wm_tail_trunc(vx.w));
-        } else {
+        {
           float tx[4] = {vx.x, vx.y, vx.z, vx.w};
           if (a.pro) {
             const float4 pa4 = *reinterpret_cast<const float4*>(&s_pa[g * 128 + col]);
@@ -335,7 +324,7 @@ int sb_wgrad_tc_tma_launch(const float* gy, int64_t ldg, const float* x, int64_t
   if (wm_make_map(&tmg, gy, ldg, R, G) != SB_OK || wm_make_map(&tmx, x, ldx, R, G) != SB_OK) return SB_ERR_UNSUPPORTED;
   WgTmaArgs a;
   a.g = gy; a.ldg = ldg; a.x = x; a.ldx = ldx; a.R = R; a.G = G; a.N = N; a.K = K; a.KP = 128;
-  a.pro = pro; a.pa = pa; a.pc = pc; a.rawhead = 0;
+  a.pro = pro; a.pa = pa; a.pc = pc;
   const long long nch = sb_ceil_div(R, WM_ROWS) * G;
   long long grid = sb_num_sms();
   if (grid > nch) grid = nch;

@@ -219,6 +219,28 @@ int sb_gine_agg_fwd(const float* x, const float* e, const float* eps, const int3
 int sb_gine_agg_bwd(const float* dA, const float* x, const float* e, const float* eps, const int64_t* edge_index,
                     const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_eid, int64_t N, int64_t E,
                     int32_t ld, float* dx, float* de, double* deps, void* stream);
+/* ---- the GINE layer stack of the predictor behind two calls (csrc/gine_stack.cu) ---------------------------------------
+ * The loop of GNN.forward (Alchemy/sign_net/model.py:44-57): L x { edge_encoder(edge_attr) -> GINEConv (aggregate + 2-layer
+ * MLP with BN/ReLU in between) -> BN -> ReLU -> + previous }, and its backward: the same entry points in the same order as
+ * the Python modules issue them one by one, enqueued back to back by host C++.  HOST tables (read during the call):
+ *   graph_ptrs[9] = { in_ptr, in_src, in_eid, out_ptr, out_dst, out_eid, edge_index, edge_attr, embedding flags|NULL }
+ *   graph_ints[8] = { N, E, ld_ea (row stride of edge_attr in elements), d, ld, nfe (continuous edge features; 0 = discrete),
+ *                     F (discrete edge-feature columns, <= 4), V (rows of an embedding table) }
+ *   fwd layer_ptrs[L][40] = { X_in, X_out, A, H, Hn, Y, Ee|0, e,  We|0, bn_e.weight|0, bn_e.bias|0, bn_e.running_mean|0,
+ *                     bn_e.running_var|0,  eps, W0, bn0.weight, bn0.bias, bn0.running_mean, bn0.running_var, W1, bn.weight,
+ *                     bn.bias, bn.running_mean, bn.running_var,  stats_e|0, stats_0|0, stats_1|0 (fp64 [2,d], zeroed by the
+ *                     caller; 0 in eval mode),  ae, ce, mre, a0, c0, mr0, a1, c1, mr1 (sb_bn_finalize outputs),
+ *                     table_0 .. table_3 (discrete edge encoder) }
+ *   bwd layer_ptrs[L][44] = { X_in, A, H, Hn, Y, Ee|0, e,  ae, ce, mre, a0, c0, mr0, a1, c1, mr1,  We|0, bn_e.weight|0, eps, W0,
+ *                     bn0.weight, W1, bn.weight,  dWe|0, dbn_e.weight|0, dbn_e.bias|0, deps (fp64 scalar, zeroed by the caller),
+ *                     dW0, dbn0.weight, dbn0.bias, dW1, dbn.weight, dbn.bias,  dtable_0 .. dtable_3, (unused) }
+ *   scratch[11]   = { Ga (in: dL/dX_L), Gb (ping-pong: dL/dX_0 ends in Ga if L is even, else Gb), dY, dH, dA, dx, de,
+ *                     stats fp64 [2,d], coef fp64 [3,d], sb_linear_wgrad workspace, sb_embedding_bwd workspace|0 } */
+int sb_gine_stack_fwd(const int64_t* layer_ptrs, int32_t L, const int64_t* graph_ptrs, const int64_t* graph_ints,
+                      int32_t training, float momentum, float bn_eps, void* stream);
+int sb_gine_stack_bwd(const int64_t* layer_ptrs, int32_t L, const int64_t* graph_ptrs, const int64_t* graph_ints,
+                      const int64_t* scratch, int32_t training, void* stream);
+
 /* ---- K10: edge-gated aggregate of the GatedGCN predictor (GraphPrediction/layers/gatedgcn_layer.py:48-54: dgl
  * apply_edges(u_add_v) + update_all(u_mul_e, sum) + update_all(copy_e, sum)) on [N, ld] node rows / [E, ld] edge rows:
  * e_out_k = (Dh[src_k] + Eh[dst_k]) + Ce_k;  h_out_i = Ah_i + sum_in(Bh[src] * sigmoid(e_out)) / (sum_in sigmoid(e_out)

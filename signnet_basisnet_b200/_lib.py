@@ -28,6 +28,8 @@ _SIGNATURES = {
     "sb_pack_neighbours": "pppp" + "l" + "p" + "p",
     "sb_gin_agg": "ppppp" + "p" + "ppppppp" + "l" + "iiiiiii" + "p",
     "sb_gin_linear_fused_fwd": "pppppp" + "ll" + "ii" + "l" + "ppppp" + "l" + "iiiii" + "p",
+    "sb_gine_stack_fwd": "pipp" + "i" + "ff" + "p",
+    "sb_gine_stack_bwd": "pippp" + "i" + "p",
     "sb_phi_stack_fwd": "ppipp" + "ii" + "ff" + "p",
     "sb_phi_stack_bwd": "ppippp" + "ii" + "p",
     "sb_linear_fwd": "pl" + "pll" + "p" + "pl" + "l" + "iii" + "ipp" + "i" + "p" + "i" + "p",

@@ -203,6 +203,22 @@ int sb_affine2(const float* t1, const float* t2, const double* coef, const doubl
 
 int sb_relu_bwd(const float* g, const float* y, float* out, int64_t n, void* stream); /* out = g * [y > 0] */
 
+/* BatchNorm + activation (+ residual) as ONE call: column statistics (training) -> a, c, mean_rstd (+ running buffers) ->
+ * out = act(a*x + c) (+ res).  nn.BatchNorm1d + ReLU + residual of elements.py:57-65, model.py:41-47,
+ * transformer_module.py / sign_net.py:70 on [M, ld] tensors.  For G = 1 and M <= 8 192 rows this is ONE kernel (a CTA owns
+ * four channels end to end; same arithmetic as the three streaming kernels, bit-identical results); otherwise it enqueues
+ * sb_col_stats -> sb_bn_finalize -> sb_affine_act_res.  stats: fp64 [G,2,C] scratch (zeroed here).
+ * sb_set_small_bn(0/1): A/B switch of the tests, returns the previous setting. */
+int sb_bn_act_fwd(const float* x, int64_t ld, int64_t M, int32_t G, int32_t C, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, float momentum, float eps, int32_t training, int32_t relu,
+                  const float* res, float* out, double* stats, float* a, float* c, double* mean_rstd, void* stream);
+/* its backward: dz (may alias gout) = d/dx, dgamma, dbeta.  stats fp64 [G,2,C], coef fp64 [3,G,C]: scratch of the
+ * streaming path (sb_bn_bwd_reduce -> sb_bn_bwd_finalize -> sb_affine2). */
+int sb_bn_act_bwd(const float* gout, const float* x, const float* a, const float* c, const double* mean_rstd,
+                  const float* gamma, int64_t ld, int64_t M, int32_t G, int32_t C, int32_t relu, int32_t training,
+                  float* dz, float* dgamma, float* dbeta, double* stats, double* coef, void* stream);
+int sb_set_small_bn(int32_t enable);
+
 /* sum over eigenvector slots and sign passes -> [N, ldo]  (sign_net.py:113 + :70 ; deepsigns.py:72-81) */
 int sb_slot_sum_fwd(const float* x, int64_t ld, int64_t R, int32_t S, const int64_t* batch, const int32_t* graph_ptr,
                     const int64_t* row_ptr, int64_t N, int32_t k, int32_t masked, int32_t limit_by_n, float* out,

@@ -60,6 +60,8 @@ _SIGNATURES = {
     "sb_layernorm_fwd": "pppp" + "ll" + "i" + "f" + "ppp" + "p",
     "sb_layernorm_bwd": "pppp" + "ll" + "i" + "pp" + "p",
     "sb_relu_bwd": "pppl" + "p",
+    "sb_bn_act_fwd": "pll" + "ii" + "pppp" + "ff" + "ii" + "pp" + "pppp" + "p",
+    "sb_bn_act_bwd": "pppppp" + "ll" + "iiii" + "ppp" + "pp" + "p",
     "sb_laplacian_evd": "pppp" + "ii" + "ppp" + "p",
     "sb_ign2to1_ops_factors": "plipiipi" + "p",
     "sb_ign2to1_ops_projectors": "piipip" + "p",
@@ -95,6 +97,8 @@ def lib():
         L.sb_set_fused_agg_linear.argtypes = [ctypes.c_int32]
         L.sb_set_small_rows.restype = ctypes.c_int
         L.sb_set_small_rows.argtypes = [ctypes.c_int32]
+        L.sb_set_small_bn.restype = ctypes.c_int
+        L.sb_set_small_bn.argtypes = [ctypes.c_int32]
         L.sb_last_linear_kernel.restype = ctypes.c_int
         L.sb_last_wgrad_kernel.restype = ctypes.c_int
         L.sb_embedding_bwd_workspace_floats.restype = ctypes.c_int64
@@ -110,7 +114,8 @@ def lib():
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["sb_last_error", "sb_abi_version", "sb_device_sm_count", "sb_gin_agg_tile_rows",
                                        "sb_linear_wgrad_workspace_floats", "sb_embedding_bwd_workspace_floats",
-                                       "sb_set_tensor_cores", "sb_set_small_rows", "sb_set_fused_agg_linear", "sb_last_linear_kernel",
+                                       "sb_set_tensor_cores", "sb_set_small_rows", "sb_set_small_bn",
+                                       "sb_set_fused_agg_linear", "sb_last_linear_kernel",
                                        "sb_last_wgrad_kernel"])
 
 

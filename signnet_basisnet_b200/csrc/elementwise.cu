@@ -517,3 +517,240 @@ extern "C" int sb_relu_bwd(const float* g, const float* y, float* out, int64_t n
   SB_CHECK_LAUNCH("sb_relu_bwd");
   return SB_OK;
 }
+
+// =====================================================================================================================
+// BatchNorm + activation as ONE call (and, for small tensors, ONE kernel).
+// The predictor / rho / encoder side of the path normalises [N, d] tensors with a few thousand rows: three launches
+// (column sums, finalize, apply) of ~4 us each per BatchNorm forward and four per backward are pure launch latency there
+// (cfg 2, the reference's Alchemy configuration: ~1100 launches for a step of ~5 ms of GPU work).  For M <= 8192 rows and
+// one group a CTA owns four channels end to end: fp64 column sums over all rows, the affine coefficients (+ running
+// buffers), then the apply pass over the same rows (L2-resident).  Larger tensors take the streaming kernels above.
+#define BN_SMALL_MAX_ROWS 8192
+
+__device__ __forceinline__ void bn_small_reduce8(double (&v)[8], double* red /*[8 warps][8]*/) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = warp_sum_d(v[j]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp * 8 + j] = v[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double t = 0.0;
+    for (int w = 0; w < EW_THREADS / 32; ++w) t += red[w * 8 + threadIdx.x];
+    red[64 + threadIdx.x] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = red[64 + j];
+}
+
+__global__ void __launch_bounds__(EW_THREADS) bn_act_small_fwd_kernel(
+    const float* __restrict__ x, long long ld, long long M, int C, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+    float eps, int training, int relu, const float* __restrict__ res, float* __restrict__ out, float* __restrict__ a,
+    float* __restrict__ c, double* __restrict__ mean_rstd) {
+  __shared__ double red[72];
+  __shared__ float sa[4], sc[4];
+  const int col0 = blockIdx.x * 4;
+  double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (training) {
+    for (long long r = threadIdx.x; r < M; r += EW_THREADS) {
+      const float4 t = ldg4(x + r * ld + col0);
+      v[0] += (double)t.x; v[1] += (double)t.y; v[2] += (double)t.z; v[3] += (double)t.w;
+      v[4] += (double)t.x * (double)t.x; v[5] += (double)t.y * (double)t.y;
+      v[6] += (double)t.z * (double)t.z; v[7] += (double)t.w * (double)t.w;
+    }
+    bn_small_reduce8(v, red);
+  }
+  if (threadIdx.x < 4) {
+    const int ch = col0 + threadIdx.x;
+    float av = 0.f, cv = 0.f;
+    if (ch < C) {   // same arithmetic as bn_finalize_kernel
+      const double gm = gamma ? (double)gamma[ch] : 1.0, bt = beta ? (double)beta[ch] : 0.0;
+      double mean, var;
+      if (training) {
+        mean = red[64 + threadIdx.x] / (double)M;
+        var = red[68 + threadIdx.x] / (double)M - mean * mean;
+        if (var < 0.0) var = 0.0;
+        if (running_mean) {
+          const double unb = (M > 1) ? var * ((double)M / (double)(M - 1)) : var;
+          running_mean[ch] = (float)((1.0 - (double)momentum) * (double)running_mean[ch] + (double)momentum * mean);
+          running_var[ch] = (float)((1.0 - (double)momentum) * (double)running_var[ch] + (double)momentum * unb);
+        }
+      } else {
+        mean = (double)running_mean[ch];
+        var = (double)running_var[ch];
+      }
+      const double rstd = 1.0 / sqrt(var + (double)eps);
+      const double avd = gm * rstd;
+      av = (float)avd;
+      cv = (float)(bt - mean * avd);
+      a[ch] = av;
+      c[ch] = cv;
+      if (mean_rstd) { mean_rstd[ch] = mean; mean_rstd[C + ch] = rstd; }
+    }
+    sa[threadIdx.x] = av;
+    sc[threadIdx.x] = cv;
+  }
+  __syncthreads();
+  const float a4[4] = {sa[0], sa[1], sa[2], sa[3]}, c4[4] = {sc[0], sc[1], sc[2], sc[3]};
+  for (long long r = threadIdx.x; r < M; r += EW_THREADS) {
+    const float4 t = ldg4(x + r * ld + col0);
+    float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (res) rr = ldg4(res + r * ld + col0);
+    const float in[4] = {t.x, t.y, t.z, t.w}, rv[4] = {rr.x, rr.y, rr.z, rr.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // same arithmetic as affine_act_res_kernel
+      if (col0 + j < C) {
+        float u = fmaf(a4[j], in[j], c4[j]);
+        if (relu) u = fmaxf(u, 0.f);
+        o[j] = u + rv[j];
+      } else {
+        o[j] = 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(out + r * ld + col0) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) bn_act_small_bwd_kernel(
+    const float* gout, const float* __restrict__ x, const float* __restrict__ pa, const float* __restrict__ pc,
+    const double* __restrict__ mean_rstd, const float* __restrict__ gamma, long long ld, long long M, int C, int relu,
+    int training, float* dz, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double red[72];
+  __shared__ float tab[8][4];   // al.hi, al.lo, be.hi, be.lo, ga.hi, ga.lo, mu.hi, mu.lo per channel
+  const int col0 = blockIdx.x * 4;
+  float a4[4], c4[4];
+  double m4[4], r4[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool ok = col0 + j < C;
+    a4[j] = ok ? __ldg(pa + col0 + j) : 0.f;
+    c4[j] = ok ? __ldg(pc + col0 + j) : 0.f;
+    m4[j] = ok ? mean_rstd[col0 + j] : 0.0;
+    r4[j] = ok ? mean_rstd[C + col0 + j] : 0.0;
+  }
+  double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (long long r = threadIdx.x; r < M; r += EW_THREADS) {   // same arithmetic as bn_bwd_reduce_kernel
+    const float4 g4 = *reinterpret_cast<const float4*>(gout + r * ld + col0);
+    const float4 y4 = ldg4(x + r * ld + col0);
+    const float gi[4] = {g4.x, g4.y, g4.z, g4.w}, yi[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float d = gi[j];
+      if (relu && !(fmaf(a4[j], yi[j], c4[j]) > 0.f)) d = 0.f;
+      if (col0 + j >= C) d = 0.f;
+      v[j] += (double)d;
+      v[4 + j] += (double)d * (((double)yi[j] - m4[j]) * r4[j]);
+    }
+  }
+  bn_small_reduce8(v, red);
+  if (threadIdx.x < 4) {   // same arithmetic as bn_bwd_finalize_kernel (G = 1)
+    const int ch = col0 + threadIdx.x;
+    F2 al = {0.f, 0.f}, be = al, ga = al, mu = al;
+    if (ch < C) {
+      const double s1 = red[64 + threadIdx.x], s2 = red[68 + threadIdx.x];
+      const double gm = gamma ? (double)gamma[ch] : 1.0;
+      const double rs = mean_rstd[C + ch];
+      const double av = gm * rs;
+      double bev = 0.0, gav = 0.0;
+      if (training) {
+        const double m1 = s1 / (double)M, m2 = s2 / (double)M;
+        bev = -av * rs * m2;
+        gav = -av * m1;
+      }
+      if (dgamma) dgamma[ch] = (float)s2;
+      if (dbeta) dbeta[ch] = (float)s1;
+      al = split_d(av); be = split_d(bev); ga = split_d(gav); mu = split_d(mean_rstd[ch]);
+    }
+    tab[0][threadIdx.x] = al.hi; tab[1][threadIdx.x] = al.lo; tab[2][threadIdx.x] = be.hi; tab[3][threadIdx.x] = be.lo;
+    tab[4][threadIdx.x] = ga.hi; tab[5][threadIdx.x] = ga.lo; tab[6][threadIdx.x] = mu.hi; tab[7][threadIdx.x] = mu.lo;
+  }
+  __syncthreads();
+  float k[8][4];
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k[q][j] = tab[q][j];
+  for (long long r = threadIdx.x; r < M; r += EW_THREADS) {   // same arithmetic as affine2_kernel
+    const float4 g4 = *reinterpret_cast<const float4*>(gout + r * ld + col0);
+    const float4 y4 = ldg4(x + r * ld + col0);
+    float u[4] = {g4.x, g4.y, g4.z, g4.w};
+    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (relu && !(fmaf(a4[j], yv[j], c4[j]) > 0.f)) u[j] = 0.f;
+      const float d = (yv[j] - k[6][j]) - k[7][j];
+      float acc = fmaf(k[3][j], d, k[5][j]);
+      acc = fmaf(k[1][j], u[j], acc);
+      acc = fmaf(k[2][j], d, acc + k[4][j]);
+      o[j] = fmaf(k[0][j], u[j], acc);
+    }
+    *reinterpret_cast<float4*>(dz + r * ld + col0) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+static int g_bn_small = 1;
+extern "C" int sb_set_small_bn(int32_t enable) {
+  const int old = g_bn_small;
+  g_bn_small = enable ? 1 : 0;
+  return old;
+}
+static bool bn_small_ok(const void* x, int64_t ld, int64_t M, int32_t G) {
+  return g_bn_small && G == 1 && M >= 1 && M <= BN_SMALL_MAX_ROWS && (ld % 4 == 0) && ((uintptr_t)x % 16 == 0);
+}
+
+// out = act(BN(x)) (+ res): column statistics (training) -> a, c, mean_rstd (+ running buffers) -> apply.
+// stats: fp64 [G,2,C] scratch (only touched by the streaming path; zeroed here).
+extern "C" int sb_bn_act_fwd(const float* x, int64_t ld, int64_t M, int32_t G, int32_t C, const float* gamma,
+                             const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                             int32_t training, int32_t relu, const float* res, float* out, double* stats, float* a, float* c,
+                             double* mean_rstd, void* stream) {
+  SB_CHECK_ARG(x && out && a && c && G >= 1 && C >= 1 && ld >= C, "sb_bn_act_fwd: bad arguments");
+  SB_CHECK_ARG(training ? (M >= 1) : (running_mean && running_var), "sb_bn_act_fwd: eval needs running statistics");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bn_small_ok(x, ld, M, G) && ((uintptr_t)out % 16 == 0) && (!res || (uintptr_t)res % 16 == 0)) {
+    bn_act_small_fwd_kernel<<<(unsigned)(ld / 4), EW_THREADS, 0, st>>>(x, ld, M, C, gamma, beta, running_mean, running_var,
+                                                                       momentum, eps, training, relu, res, out, a, c,
+                                                                       mean_rstd);
+    SB_CHECK_LAUNCH("sb_bn_act_fwd(small)");
+    return SB_OK;
+  }
+  if (training) {
+    SB_CHECK_ARG(stats != nullptr, "sb_bn_act_fwd: stats scratch required");
+    SB_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)G * 2 * C, st));
+    const int rc = sb_col_stats(x, ld, M, G, C, stats, stream);
+    if (rc) return rc;
+  }
+  int rc = sb_bn_finalize(training ? stats : nullptr, M, G, C, gamma, beta, running_mean, running_var, momentum, eps,
+                          training, a, c, mean_rstd, stream);
+  if (rc) return rc;
+  return sb_affine_act_res(x, a, c, res, out, ld, M, G, C, relu, stream);
+}
+
+// dz (may alias gout) <- d/dx of act(BN(x)) given gout; dgamma, dbeta.  stats fp64 [G,2,C] and coef fp64 [3,G,C]: scratch of
+// the streaming path.
+extern "C" int sb_bn_act_bwd(const float* gout, const float* x, const float* a, const float* c, const double* mean_rstd,
+                             const float* gamma, int64_t ld, int64_t M, int32_t G, int32_t C, int32_t relu,
+                             int32_t training, float* dz, float* dgamma, float* dbeta, double* stats, double* coef,
+                             void* stream) {
+  SB_CHECK_ARG(gout && x && a && c && mean_rstd && dz && G >= 1 && C >= 1, "sb_bn_act_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bn_small_ok(x, ld, M, G) && ((uintptr_t)gout % 16 == 0) && ((uintptr_t)dz % 16 == 0)) {
+    bn_act_small_bwd_kernel<<<(unsigned)(ld / 4), EW_THREADS, 0, st>>>(gout, x, a, c, mean_rstd, gamma, ld, M, C, relu,
+                                                                       training, dz, dgamma, dbeta);
+    SB_CHECK_LAUNCH("sb_bn_act_bwd(small)");
+    return SB_OK;
+  }
+  SB_CHECK_ARG(stats && coef, "sb_bn_act_bwd: scratch required");
+  SB_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)G * 2 * C, st));
+  int rc = sb_bn_bwd_reduce(gout, x, a, c, mean_rstd, nullptr, ld, M, G, C, relu, stats, stream);
+  if (rc) return rc;
+  rc = sb_bn_bwd_finalize(stats, M, G, C, gamma, mean_rstd, training, 0, dgamma, dbeta, coef, stream);
+  if (rc) return rc;
+  return sb_affine2(gout, x, coef, mean_rstd, relu ? a : nullptr, relu ? c : nullptr, dz, ld, M, G, C, stream);
+}

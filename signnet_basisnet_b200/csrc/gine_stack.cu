@@ -41,25 +41,13 @@ Gr read_gr(const int64_t* p, const int64_t* n) {
 int bn_act(const float* x, float* out, const float* res, int64_t M, int ld, int C, const float* gamma, const float* beta,
            float* rm, float* rv, double* stats, float* a, float* c, double* mr, int training, float mom, float eps,
            void* st) {
-  int rc = SB_OK;
-  if (training) {
-    rc = sb_col_stats(x, ld, M, 1, C, stats, st);
-    if (rc) return rc;
-  }
-  rc = sb_bn_finalize(training ? stats : nullptr, M, 1, C, gamma, beta, rm, rv, mom, eps, training, a, c, mr, st);
-  if (rc) return rc;
-  return sb_affine_act_res(x, a, c, res, out, ld, M, 1, C, 1, st);
+  return sb_bn_act_fwd(x, ld, M, 1, C, gamma, beta, rm, rv, mom, eps, training, 1, res, out, stats, a, c, mr, st);
 }
 // BatchNormActFn.backward: dz (may alias gout) <- d/dx of relu(BN(x)); dgamma, dbeta
 int bn_act_bwd(const float* gout, const float* x, const float* a, const float* c, const double* mr, const float* gamma,
                int64_t M, int ld, int C, int training, float* dz, float* dgamma, float* dbeta, double* stats, double* coef,
                cudaStream_t st) {
-  SB_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)C, st));
-  int rc = sb_bn_bwd_reduce(gout, x, a, c, mr, nullptr, ld, M, 1, C, 1, stats, st);
-  if (rc) return rc;
-  rc = sb_bn_bwd_finalize(stats, M, 1, C, gamma, mr, training, 0, dgamma, dbeta, coef, st);
-  if (rc) return rc;
-  return sb_affine2(gout, x, coef, mr, a, c, dz, ld, M, 1, C, st);
+  return sb_bn_act_bwd(gout, x, a, c, mr, gamma, ld, M, 1, C, 1, training, dz, dgamma, dbeta, stats, coef, (void*)st);
 }
 }  // namespace
 

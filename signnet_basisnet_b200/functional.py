@@ -144,13 +144,14 @@ class BatchNormActFn(torch.autograd.Function):
         if ld % 4 != 0:
             raise ValueError("batch_norm_act expects a padded activation (ld % 4 == 0)")
         dev = x.device
-        stats = None
-        if training:
-            stats = torch.zeros(G, 2, C, dtype=torch.float64, device=dev)
-            _call("sb_col_stats", _p(x), ld, M, G, C, _p(stats))
-        a, c, mr = bn_finalize(stats, M, G, C, gamma, beta, rmean, rvar, training, dev)
+        ac = torch.empty(2, G, C, dtype=torch.float32, device=dev)
+        a, c = ac[0], ac[1]
+        # fp64 [G,2,C] scratch of the streaming path followed by mean_rstd [2,G,C]; ONE C-ABI call (one kernel when small)
+        f64 = torch.empty(2, 2, G, C, dtype=torch.float64, device=dev)
+        mr = f64[1]
         out = torch.empty_like(x)
-        _call("sb_affine_act_res", _p(x), _p(a), _p(c), _p(res), _p(out), ld, M, G, C, int(relu))
+        _call("sb_bn_act_fwd", _p(x), ld, M, G, C, _p(gamma), _p(beta), _p(rmean), _p(rvar), BN_MOMENTUM, BN_EPS,
+              int(training), int(relu), _p(res), _p(out), _p(f64[0]), _p(a), _p(c), _p(mr))
         ctx.save_for_backward(x, a, c, mr, gamma)
         ctx.cfg = (training, relu, C, res is not None, G)
         return out
@@ -162,7 +163,11 @@ class BatchNormActFn(torch.autograd.Function):
         gout = gout.contiguous()
         M, ld = x.shape[-2], x.shape[-1]
         gx = torch.empty_like(x)
-        dgamma, dbeta = bn_backward(gout, x, a, c, mr, gamma, ld, M, G, C, relu, training, gx)
+        dgb = torch.empty(2, C, dtype=torch.float32, device=x.device)
+        f64 = torch.empty(5, G, C, dtype=torch.float64, device=x.device)   # stats [G,2,C] | coef [3,G,C]
+        _call("sb_bn_act_bwd", _p(gout), _p(x), _p(a), _p(c), _p(mr), _p(gamma), ld, M, G, C, int(relu), int(training),
+              _p(gx), _p(dgb[0]), _p(dgb[1]), _p(f64[:2]), _p(f64[2:]))
+        dgamma, dbeta = dgb[0], dgb[1]
         return gx, dgamma, dbeta, (gout if has_res else None), None, None, None, None, None, None
 
 

@@ -253,3 +253,69 @@ def test_linear_fwd_streaming_sizes(K, N, pro, relu, bias):
                                      (70, 96, 2)])
 def test_linear_wgrad_streaming_sizes(K, N, pro):
     test_linear_wgrad(K, N, pro, R=2999)
+
+
+@pytest.mark.parametrize("M,C,relu,res,training", [(2922, 64, True, True, True), (333, 95, True, False, True),
+                                                   (8192, 128, False, False, True), (1, 6, True, True, True),
+                                                   (700, 67, True, True, False)])
+def test_bn_act_small_kernel_matches_streaming_and_torch(M, C, relu, res, training):
+    """sb_bn_act_fwd / sb_bn_act_bwd: the one-kernel path (<= 8 192 rows) is bit-identical to the three streaming kernels
+    it replaces, and both are nn.BatchNorm1d (+ ReLU + residual) within 1e-5 (forward, input / affine gradients,
+    running buffers)."""
+    from signnet_basisnet_b200 import _lib
+    from signnet_basisnet_b200.functional import batch_norm_act
+    from signnet_basisnet_b200.layout import pad4
+
+    torch.manual_seed(M + C)
+    ld = pad4(C)
+    x0 = torch.zeros(M, ld)
+    x0[:, :C] = torch.randn(M, C) * 1.7 + 0.3
+    r0 = torch.zeros(M, ld)
+    r0[:, :C] = torch.randn(M, C)
+    g0 = torch.zeros(M, ld)
+    g0[:, :C] = torch.randn(M, C)
+    bn_ref = torch.nn.BatchNorm1d(C)
+    with torch.no_grad():
+        bn_ref.weight.copy_(torch.rand(C) + 0.5)
+        bn_ref.bias.copy_(torch.randn(C) * 0.2)
+        bn_ref.running_mean.copy_(torch.randn(C) * 0.1)
+        bn_ref.running_var.copy_(torch.rand(C) + 0.5)
+    bn_ref.train(training)
+    sd = {k: v.clone() for k, v in bn_ref.state_dict().items()}
+
+    def run(small):
+        old = _lib.lib().sb_set_small_bn(small)
+        try:
+            bn = torch.nn.BatchNorm1d(C).to(DEV)
+            bn.load_state_dict(sd)
+            bn.train(training)
+            x = x0.to(DEV).requires_grad_(True)
+            r = r0.to(DEV).requires_grad_(True) if res else None
+            out = batch_norm_act(x, bn, training, relu=relu, res=r)
+            out.backward(g0.to(DEV))
+            torch.cuda.synchronize()
+            return [out.detach().cpu(), x.grad.cpu(), bn.weight.grad.cpu(), bn.bias.grad.cpu(), bn.running_mean.cpu(),
+                    bn.running_var.cpu()] + ([r.grad.cpu()] if res else [])
+        finally:
+            _lib.lib().sb_set_small_bn(old)
+
+    a, b = run(1), run(0)
+    for i, (u, v) in enumerate(zip(a, b)):
+        assert torch.equal(u, v), (i, float((u - v).abs().max()))
+    if M > 1:
+        xr = x0[:, :C].double().requires_grad_(True)
+        bn64 = torch.nn.BatchNorm1d(C).double()
+        bn64.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()})
+        bn64.train(training)
+        y = bn64(xr)
+        y = y.relu() if relu else y
+        if res:
+            y = y + r0[:, :C].double()
+        y.backward(g0[:, :C].double())
+        assert_close_rel(a[0][:, :C].double(), y.detach(), 1e-5, what="bn_act out")
+        assert_close_rel(a[1][:, :C].double(), xr.grad, 1e-5, what="bn_act dx")
+        assert_close_rel(a[2].double(), bn64.weight.grad, 1e-5, what="bn_act dgamma")
+        assert_close_rel(a[3].double(), bn64.bias.grad, 1e-5, what="bn_act dbeta")
+        assert_close_rel(a[4].double(), bn64.running_mean, 1e-5, what="running_mean")
+        assert_close_rel(a[5].double(), bn64.running_var, 1e-5, what="running_var")
+    assert float(a[0][:, C:].abs().max()) == 0.0 if ld > C else True

@@ -330,6 +330,10 @@ int sb_attention_bwd(const float* q, const float* k, const float* v, const float
                      const int64_t* batch, const int32_t* graph_ptr, const int64_t* row_ptr, int64_t N,
                      int32_t kslots, int32_t masked, int32_t kmax, int32_t n_head, int32_t dk, float temperature,
                      float drop_p, int64_t seed, float* gq, float* gk, float* gv, void* stream);
+/* 1 (default): d_k = 32, k_b <= 40, 16-byte aligned rows run on the tensor-core kernels of csrc/attention_mma.cu
+ * (warp per (node, head), mma.sync m16n8k8 3xTF32, fragments straight from global memory); 0: the FFMA kernels of
+ * csrc/attention_fast.cu (which every other shape takes anyway).  Returns the previous setting (A/B switch of the tests). */
+int sb_set_attention_mma(int32_t enable);
 /* y = LayerNorm(a + b) * w + beta per row (MaskedLN, masked_layers.py:22-32, eps 1e-6); xsum = a + b and
  * stat[R,2] = (mean, rstd) are kept for the backward; dwb[2,C] (fp64) accumulates (dw, dbeta). */
 int sb_layernorm_fwd(const float* a, const float* b, const float* w, const float* beta, int64_t ld, int64_t R,

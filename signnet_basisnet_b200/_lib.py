@@ -97,6 +97,8 @@ def lib():
         L.sb_set_fused_agg_linear.argtypes = [ctypes.c_int32]
         L.sb_set_small_rows.restype = ctypes.c_int
         L.sb_set_small_rows.argtypes = [ctypes.c_int32]
+        L.sb_set_attention_mma.restype = ctypes.c_int
+        L.sb_set_attention_mma.argtypes = [ctypes.c_int32]
         L.sb_set_small_bn.restype = ctypes.c_int
         L.sb_set_small_bn.argtypes = [ctypes.c_int32]
         L.sb_last_linear_kernel.restype = ctypes.c_int
@@ -114,7 +116,7 @@ def lib():
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["sb_last_error", "sb_abi_version", "sb_device_sm_count", "sb_gin_agg_tile_rows",
                                        "sb_linear_wgrad_workspace_floats", "sb_embedding_bwd_workspace_floats",
-                                       "sb_set_tensor_cores", "sb_set_small_rows", "sb_set_small_bn",
+                                       "sb_set_tensor_cores", "sb_set_small_rows", "sb_set_small_bn", "sb_set_attention_mma",
                                        "sb_set_fused_agg_linear", "sb_last_linear_kernel",
                                        "sb_last_wgrad_kernel"])
 

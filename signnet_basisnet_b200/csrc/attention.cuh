@@ -38,3 +38,6 @@ __device__ __forceinline__ float att_keep_scale(unsigned long long seed, long lo
 // fast path: k_b <= 40 tokens, d_k <= 32 (covers every shipped configuration); SB_ERR_UNSUPPORTED otherwise
 int sb_attention_fast_fwd_launch(const AttArgs& a, int kmax, cudaStream_t st);
 int sb_attention_fast_bwd_launch(const AttArgs& a, int kmax, cudaStream_t st);
+// tensor-core path (attention_mma.cu): d_k == 32, k_b <= 40, 16-byte aligned rows; SB_ERR_UNSUPPORTED otherwise
+int sb_attention_mma_fwd_launch(const AttArgs& a, int kmax, cudaStream_t st);
+int sb_attention_mma_bwd_launch(const AttArgs& a, int kmax, cudaStream_t st);

@@ -157,6 +157,10 @@ extern "C" int sb_attention_fwd(const float* q, const float* k, const float* v, 
   a.kslots = kslots; a.masked = masked; a.n_head = n_head; a.dk = dk; a.inv_temp_div = temperature;
   a.drop_p = drop_p; a.seed = (unsigned long long)seed; a.o = o; a.go = nullptr; a.gq = a.gk = a.gv = nullptr;
   {
+    const int rc = sb_attention_mma_fwd_launch(a, kmax, (cudaStream_t)stream);
+    if (rc != SB_ERR_UNSUPPORTED) return rc;
+  }
+  {
     const int rc = sb_attention_fast_fwd_launch(a, kmax, (cudaStream_t)stream);
     if (rc != SB_ERR_UNSUPPORTED) return rc;
   }
@@ -180,6 +184,10 @@ extern "C" int sb_attention_bwd(const float* q, const float* k, const float* v, 
   a.q = q; a.k = k; a.v = v; a.ld = ld; a.batch = batch; a.graph_ptr = graph_ptr; a.row_ptr = row_ptr; a.N = N;
   a.kslots = kslots; a.masked = masked; a.n_head = n_head; a.dk = dk; a.inv_temp_div = temperature;
   a.drop_p = drop_p; a.seed = (unsigned long long)seed; a.o = nullptr; a.go = go; a.gq = gq; a.gk = gk; a.gv = gv;
+  {
+    const int rc = sb_attention_mma_bwd_launch(a, kmax, (cudaStream_t)stream);
+    if (rc != SB_ERR_UNSUPPORTED) return rc;
+  }
   {
     const int rc = sb_attention_fast_bwd_launch(a, kmax, (cudaStream_t)stream);
     if (rc != SB_ERR_UNSUPPORTED) return rc;

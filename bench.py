@@ -178,9 +178,10 @@ def run_b200(args):
     # End to end: every step copies ITS batch host -> device from pinned memory (on a copy stream, issued one step ahead
     # like a prefetching DataLoader would, so the transfer overlaps the previous step's backward) and reads the loss back.
     pending = []
-    loss_pin = torch.empty(2, dtype=torch.float32).pin_memory()
-    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
-    e2e_state = {"i": 0, "losses": []}
+    LOSS_LAG, LOSS_RING = 3, 4
+    loss_pin = torch.empty(LOSS_RING, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(blocking=True) for _ in range(LOSS_RING)]
+    e2e_state = {"i": 0, "losses": [], "read": 0, "split": []}
 
     def fetch():
         with torch.cuda.stream(copy_stream):
@@ -191,22 +192,35 @@ def run_b200(args):
     def step_e2e():
         if not pending:
             fetch()
+        t0_ = time.perf_counter()
         data = pending.pop(0)
         for v in data.__dict__.values():
             if torch.is_tensor(v):
                 v.record_stream(torch.cuda.current_stream())
         fetch()  # next step's batch
+        t1_ = time.perf_counter()
         # D2H read of the loss, every step, without draining the launch pipeline: the scalar goes to pinned host memory
-        # with an asynchronous copy and is read one step later, once its event has completed (what a training loop that
-        # logs the loss does when it does not want `.item()` to stall the next step's launches)
+        # with an asynchronous copy and is consumed LOSS_LAG steps later, once its event has completed (what a training
+        # loop that logs the loss does when `.item()` must not stall the next step's launches; a host-side hiccup of the
+        # shared box then no longer idles the GPU).  Every loss of the timed region is read before its closing barrier.
         loss = step(data)
         i = e2e_state["i"]
         e2e_state["i"] = i + 1
-        loss_pin[i & 1].copy_(loss.detach(), non_blocking=True)
-        loss_ev[i & 1].record()
-        if i > 0:
-            loss_ev[(i - 1) & 1].synchronize()
-            e2e_state["losses"].append(float(loss_pin[(i - 1) & 1]))
+        loss_pin[i % LOSS_RING].copy_(loss.detach(), non_blocking=True)
+        loss_ev[i % LOSS_RING].record()
+        t2_ = time.perf_counter()
+        if i >= LOSS_LAG:
+            drain_loss(i - LOSS_LAG)
+        e2e_state["split"].append((t1_ - t0_, t2_ - t1_, time.perf_counter() - t2_))
+
+    def drain_loss(j):
+        loss_ev[j % LOSS_RING].synchronize()
+        e2e_state["losses"].append(float(loss_pin[j % LOSS_RING]))
+        e2e_state["read"] = j + 1
+
+    def drain_all():
+        for j in range(e2e_state.get("read", 0), e2e_state["i"]):
+            drain_loss(j)
 
     ring = twin(resident)
     pos = [0]
@@ -223,7 +237,7 @@ def run_b200(args):
 
     import gc
 
-    def timed(fn, n):
+    def timed(fn, n, after=None):
         # the cyclic collector is paused inside a timed region (a full collection of this process is a 10-20 ms pause
         # that lands in one random step of a 20-step window); reference cycles wait until the region ends
         gc.collect()
@@ -231,12 +245,12 @@ def run_b200(args):
         if os.environ.get("SB_BENCH_GC") != "1":
             gc.disable()
         try:
-            return _timed(fn, n)
+            return _timed(fn, n, after)
         finally:
             if gc_was:
                 gc.enable()
 
-    def _timed(fn, n):
+    def _timed(fn, n, after=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -246,6 +260,8 @@ def run_b200(args):
             t_ = time.perf_counter()
             fn()
             tt.append(time.perf_counter() - t_)
+        if after is not None:
+            after()   # still inside the timed region (e.g. the e2e loop's outstanding loss reads)
         e1.record()
         if dbg:
             st_ = torch.cuda.memory_stats()
@@ -271,7 +287,10 @@ def run_b200(args):
     launches = _lib.launch_count - c0
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, args.steps, after=drain_all)
+    if os.environ.get("SB_BENCH_DEBUG") == "1":
+        sys.stderr.write("e2e host ms per step (fetch | step | loss wait): " + " ".join(
+            f"{1e3 * a_:.0f}|{1e3 * b_:.0f}|{1e3 * c_:.0f}" for a_, b_, c_ in e2e_state["split"][-args.steps:]) + "\n")
 
     # N > 1: (a) what the gradient exchange costs after overlap = step time with it minus step time without it;
     # (b) strong scaling, BASELINE.json configs[3] as written: ONE global batch of --batch graphs sharded over the GPUs
@@ -382,7 +401,7 @@ def run_b200(args):
         "config": workload_config(args.batch, world, gi.N, gi.E),
         "e2e": {"value": round(graphs / (ms_e2e * 1e-3), 1), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3),
-                "loss_read": "every step, async copy to pinned memory, consumed one step later (all inside the timed region)",
+                "loss_read": "every step, async copy to pinned memory, consumed 3 steps later (all inside the timed region)",
                 "losses_read": len(e2e_state["losses"])},
         "gpu_launches": launches, "gpu_launches_note": "C-ABI entry-point calls inside the timed region (each "
                                                         "enqueues >= 1 kernel of libsignnet_b200.so)",

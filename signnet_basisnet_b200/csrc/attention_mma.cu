@@ -302,15 +302,22 @@ __global__ void __launch_bounds__(32 * AM_WARPS, MINB) attention_mma_fwd_kernel(
   }
 }
 
+#define AM_TR_ROWS 48      // query rows kept per warp (3 row tiles)
+#define AM_TR_LD 44        // row stride of the transposition buffers: 2*44 = 24 (mod 32) -> phase B's reads hit 32 banks
+#define AM_BWD_SMEM (AM_WARPS * 2 * AM_TR_ROWS * AM_TR_LD * (int)sizeof(float))
+
+// Backward.  Phase A (rows = queries): S = (Q/T) K^T and dP = dO V^T -> P, D = sum_j2 dP P, dS = P (dP - D), dQ = dS K / T;
+// Pdrop and dS are also written to shared memory [query][key].  Phase B (rows = keys) reads them back TRANSPOSED as the
+// A fragments of dV = Pdrop^T dO and dK = dS^T (Q/T): no recomputation of the scores (the first version recomputed
+// S^T = K Q^T and dP^T = V dO^T with the operands swapped: two of seven contractions, their loads, splits and exp2).
 template <int MINB>
 __global__ void __launch_bounds__(32 * AM_WARPS, MINB) attention_mma_bwd_kernel(const AttArgs a) {
-  __shared__ float stat[AM_WARPS][3][48];
+  extern __shared__ __align__(16) float am_smem[];
   AmCtx c;
   if (!am_ctx(a, c)) return;
   const int warp = threadIdx.x >> 5;
-  float* Ms = stat[warp][0];   // row max
-  float* Ls = stat[warp][1];   // 1 / row sum
-  float* Ds = stat[warp][2];   // sum_j2 dP P
+  float* Pt = am_smem + (size_t)warp * 2 * AM_TR_ROWS * AM_TR_LD;   // Pdrop[j1][j2]
+  float* St = Pt + AM_TR_ROWS * AM_TR_LD;                            // dS[j1][j2]
   const float* qp = a.q + c.r0;
   const float* kp = a.k + c.r0;
   const float* vp = a.v + c.r0;
@@ -322,7 +329,7 @@ __global__ void __launch_bounds__(32 * AM_WARPS, MINB) attention_mma_bwd_kernel(
   prefetch_rows(gp, c.rs, kb);
   prefetch_rows(kp, c.rs, kb);
   prefetch_rows(vp, c.rs, kb);
-  // ---- phase A: rows = queries.  S = (Q/T) K^T, dP = dO V^T -> P, D = sum_j2 dP P, dS = P (dP - D); dQ = dS K / T
+  // ---- phase A
   for (int mt = 0; mt * 16 < kb; ++mt) {
     const int ja = mt * 16 + g, jb = ja + 8;
     float s[AM_NT][4], dp[AM_NT][4];
@@ -344,17 +351,22 @@ __global__ void __launch_bounds__(32 * AM_WARPS, MINB) attention_mma_bwd_kernel(
     cols_load(kraw, kp, c);
     float ma, mb, la, lb;
     softmax_rows(s, NT, kb, t, ma, mb, la, lb);
+    const bool va = ja < kb, vb = jb < kb;   // query rows beyond the token set contribute nothing to dK / dV
     float da = 0.f, db = 0.f;
 #pragma unroll
     for (int nt = 0; nt < AM_NT; ++nt) {
       if (nt < NT) {
+        const int c0 = nt * 8 + 2 * t;
+        float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
         if (a.drop_p > 0.f) {
-          const int c0 = nt * 8 + 2 * t;
-          dp[nt][0] *= att_keep_scale(a.seed, c.node, c.h, ja, c0, a.drop_p);
-          dp[nt][1] *= att_keep_scale(a.seed, c.node, c.h, ja, c0 + 1, a.drop_p);
-          dp[nt][2] *= att_keep_scale(a.seed, c.node, c.h, jb, c0, a.drop_p);
-          dp[nt][3] *= att_keep_scale(a.seed, c.node, c.h, jb, c0 + 1, a.drop_p);
+          k0 = att_keep_scale(a.seed, c.node, c.h, ja, c0, a.drop_p);
+          k1 = att_keep_scale(a.seed, c.node, c.h, ja, c0 + 1, a.drop_p);
+          k2 = att_keep_scale(a.seed, c.node, c.h, jb, c0, a.drop_p);
+          k3 = att_keep_scale(a.seed, c.node, c.h, jb, c0 + 1, a.drop_p);
+          dp[nt][0] *= k0; dp[nt][1] *= k1; dp[nt][2] *= k2; dp[nt][3] *= k3;
         }
+        *reinterpret_cast<float2*>(Pt + ja * AM_TR_LD + c0) = va ? make_float2(s[nt][0] * k0, s[nt][1] * k1) : make_float2(0.f, 0.f);
+        *reinterpret_cast<float2*>(Pt + jb * AM_TR_LD + c0) = vb ? make_float2(s[nt][2] * k2, s[nt][3] * k3) : make_float2(0.f, 0.f);
         da = fmaf(dp[nt][0], s[nt][0], da);
         da = fmaf(dp[nt][1], s[nt][1], da);
         db = fmaf(dp[nt][2], s[nt][2], db);
@@ -363,17 +375,16 @@ __global__ void __launch_bounds__(32 * AM_WARPS, MINB) attention_mma_bwd_kernel(
     }
     da = quad_sum(da);
     db = quad_sum(db);
-    if (t == 0) {
-      Ms[ja] = ma; Ls[ja] = la; Ds[ja] = da;
-      Ms[jb] = mb; Ls[jb] = lb; Ds[jb] = db;
-    }
 #pragma unroll
     for (int nt = 0; nt < AM_NT; ++nt) {
       if (nt < NT) {
+        const int c0 = nt * 8 + 2 * t;
         s[nt][0] *= dp[nt][0] - da;
         s[nt][1] *= dp[nt][1] - da;
         s[nt][2] *= dp[nt][2] - db;
         s[nt][3] *= dp[nt][3] - db;
+        *reinterpret_cast<float2*>(St + ja * AM_TR_LD + c0) = va ? make_float2(s[nt][0], s[nt][1]) : make_float2(0.f, 0.f);
+        *reinterpret_cast<float2*>(St + jb * AM_TR_LD + c0) = vb ? make_float2(s[nt][2], s[nt][3]) : make_float2(0.f, 0.f);
       }
     }
     float dq[4][4];
@@ -381,56 +392,37 @@ __global__ void __launch_bounds__(32 * AM_WARPS, MINB) attention_mma_bwd_kernel(
     store_rows(a.gq + c.r0, c.rs, ja, jb, kb, t, dq, rT);
   }
   __syncwarp();
-  // ---- phase B: rows = keys.  S^T = K (Q/T)^T, dP^T = V dO^T (operands swapped) -> P^T, dS^T from the row statistics of
-  // phase A (now indexed by column); dV = Pdrop^T dO, dK = dS^T (Q/T)
+  // ---- phase B: rows = keys; the contraction runs over the queries 8kt + 2t, 8kt + 2t + 1 (same permutation as the
+  // column-pattern B operand)
   for (int mt = 0; mt * 16 < kb; ++mt) {
     const int ja = mt * 16 + g, jb = ja + 8;   // key rows of this lane
-    float st[AM_NT][4], dpt[AM_NT][4];
-    {
-      const Raw8 r0 = load_raw(kp + ja * c.rs, t, ja < kb), r1 = load_raw(kp + jb * c.rs, t, jb < kb);
-      const Raw8 r2 = load_raw(vp + ja * c.rs, t, ja < kb), r3 = load_raw(vp + jb * c.rs, t, jb < kb);
-      Raw8 raw[AM_NT];
-      rows_load(raw, qp, c);
-      Frag8 fa, fb;
-      split_row(fa, r0, 1.f);
-      split_row(fb, r1, 1.f);
-      rows_product(st, fa, fb, raw, NT, rTs);
-      rows_load(raw, gp, c);
-      split_row(fa, r2, 1.f);
-      split_row(fb, r3, 1.f);
-      rows_product(dpt, fa, fb, raw, NT, 1.f);
-    }
-    Raw8 graw[AM_NT];
+    Raw8 graw[AM_NT], qraw[AM_NT];
     cols_load(graw, gp, c);
+    cols_load(qraw, qp, c);
+    float acc[4][4];
 #pragma unroll
-    for (int nt = 0; nt < AM_NT; ++nt) {
-      if (nt < NT) {
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j1 = nt * 8 + 2 * t + (e & 1);        // query = column
-          const int j2 = (e & 2) ? jb : ja;               // key = row
-          float pd = 0.f, ds = 0.f;
-          if (j1 < kb && j2 < kb) {
-            const float p = exp2f(st[nt][e] - Ms[j1]) * Ls[j1];
-            float d = dpt[nt][e];
-            pd = p;
-            if (a.drop_p > 0.f) {
-              const float ks = att_keep_scale(a.seed, c.node, c.h, j1, j2, a.drop_p);
-              pd *= ks;
-              d *= ks;
-            }
-            ds = p * (d - Ds[j1]);
-          }
-          st[nt][e] = pd;
-          dpt[nt][e] = ds;
-        }
+    for (int kt = 0; kt < AM_NT; ++kt) {
+      if (kt < NT) {
+        const float* r0 = Pt + (kt * 8 + 2 * t) * AM_TR_LD;
+        const float p[4] = {ja < kb ? r0[ja] : 0.f, ja < kb ? r0[AM_TR_LD + ja] : 0.f, jb < kb ? r0[jb] : 0.f,
+                            jb < kb ? r0[AM_TR_LD + jb] : 0.f};   // key rows beyond the token set: not stored, not read
+        mma_cols(acc, p, graw[kt], 1.f);
       }
     }
-    float acc[4][4];
-    cols_product(acc, st, graw, NT, 1.f);
     store_rows(a.gv + c.r0, c.rs, ja, jb, kb, t, acc, 1.f);
-    cols_load(graw, qp, c);
-    cols_product(acc, dpt, graw, NT, rT);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < AM_NT; ++kt) {
+      if (kt < NT) {
+        const float* r0 = St + (kt * 8 + 2 * t) * AM_TR_LD;
+        const float p[4] = {ja < kb ? r0[ja] : 0.f, ja < kb ? r0[AM_TR_LD + ja] : 0.f, jb < kb ? r0[jb] : 0.f,
+                            jb < kb ? r0[AM_TR_LD + jb] : 0.f};   // key rows beyond the token set: not stored, not read
+        mma_cols(acc, p, qraw[kt], rT);
+      }
+    }
     store_rows(a.gk + c.r0, c.rs, ja, jb, kb, t, acc, 1.f);
   }
 }
@@ -466,8 +458,14 @@ int sb_attention_mma_bwd_launch(const AttArgs& a, int kmax, cudaStream_t st) {
   if (!am_ok(a, kmax, true)) return SB_ERR_UNSUPPORTED;
   dim3 grid((unsigned)a.N, (unsigned)((a.n_head + AM_WARPS - 1) / AM_WARPS));
   static const int minb = getenv("SB_ATT_BWD_MINB") ? atoi(getenv("SB_ATT_BWD_MINB")) : 3;
-  if (minb == 3) attention_mma_bwd_kernel<3><<<grid, 32 * AM_WARPS, 0, st>>>(a);
-  else attention_mma_bwd_kernel<2><<<grid, 32 * AM_WARPS, 0, st>>>(a);
+  static bool configured = false;
+  if (!configured) {
+    SB_CUDA(cudaFuncSetAttribute(attention_mma_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_BWD_SMEM));
+    SB_CUDA(cudaFuncSetAttribute(attention_mma_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_BWD_SMEM));
+    configured = true;
+  }
+  if (minb == 3) attention_mma_bwd_kernel<3><<<grid, 32 * AM_WARPS, AM_BWD_SMEM, st>>>(a);
+  else attention_mma_bwd_kernel<2><<<grid, 32 * AM_WARPS, AM_BWD_SMEM, st>>>(a);
   SB_CHECK_LAUNCH("sb_attention_bwd(mma)");
   return SB_OK;
 }

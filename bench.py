@@ -323,7 +323,7 @@ def run_b200(args):
     prof = _lib.profile_stop()
     total_prof = sum(t for _, t in prof.values()) or 1.0
     kernels = [{"entry": k, "launches_per_step": c / args.steps, "ms_per_step": t / args.steps,
-                "share": t / total_prof} for k, (c, t) in sorted(prof.items(), key=lambda kv: -kv[1][1])][:12]
+                "share": t / total_prof} for k, (c, t) in sorted(prof.items(), key=lambda kv: -kv[1][1])][:14]
 
     # roofline of the phi aggregate (K1).  SURVEY §8d: bytes = 2*4*ld*S*R + 16*E per launch (read X, write A, read the
     # int64 edge_index once).  In the default path the forward aggregate runs INSIDE gin_lin_fused_kernel, which also
@@ -367,6 +367,26 @@ def run_b200(args):
              "frac": round(alone_bytes / (t_alone * 1e-3) / 1e9 / peak, 4), "avg_launch_us": round(t_alone * 1e3, 1),
              "traffic": (tj.get("dram_bytes_per_launch") if traffic_src else None), "traffic_source": traffic_src}
     del xs, ys
+    # every phi-size streaming / contraction kernel of the step against the same measured HBM peak: algorithmic bytes
+    # (activation tensors T1 = 4*ld*S*R bytes each, as DESIGN.md §4 counts them) / CUDA-event time per launch
+    rows_phi, Tr = 2 * sl.R, 4 * ld * sl.R
+    alg = {f"sb_linear_fwd[K={ld},N={ld},rows={rows_phi}]": (2 * T1, "X in, Y out"),
+           f"sb_linear_wgrad[N={ld},K={ld},rows={rows_phi}]": (2 * T1, "dY, X in"),
+           "sb_affine2": (3 * T1, "gout, y in, dz out (BatchNorm backward, apply)"),
+           "sb_bn_bwd_reduce": (2 * T1, "gout, y in (BatchNorm backward, sums)"),
+           "sb_affine_act_res": (3 * T1, "y, residual in, x out (2 tensors for layer 0 and the rho-size calls)"),
+           "sb_gin_linear_fused_fwd": (3 * T1 + 16 * gi.E, "X in, A and H out"),
+           f"sb_gin_agg[ld={ld},bwd]": (4 * T1 + 16 * gi.E, "dA, G, X in, G out"),
+           "sb_attention_fwd": (4 * Tr, "q, k, v in, o out"),
+           "sb_attention_bwd": (7 * Tr, "q, k, v, do in, dq, dk, dv out"),
+           f"sb_linear_fwd[K={ld},N={ld},rows={sl.R}]": (2 * Tr, "X in, Y out (rho)"),
+           f"sb_linear_wgrad[N={ld},K={ld},rows={sl.R}]": (2 * Tr, "dY, X in (rho)")}
+    for kr in kernels:
+        if kr["entry"] in alg and kr["launches_per_step"] > 0:
+            nb, what = alg[kr["entry"]]
+            us = kr["ms_per_step"] / kr["launches_per_step"] * 1e3
+            kr.update({"avg_launch_us": round(us, 1), "algorithmic_bytes_per_launch": nb, "algorithmic_bytes": what,
+                       "hbm_frac": round(nb / (us * 1e-6) / 1e9 / peak, 3)})
     fused = rec("sb_gin_linear_fused_fwd", 3 * T1 + 16 * gi.E)
     fwd = rec(f"sb_gin_agg[ld={ld}]", alone_bytes)
     bwd = rec(f"sb_gin_agg[ld={ld},bwd]", 4 * T1 + 16 * gi.E)

@@ -12,4 +12,5 @@ for k in ("grad_exchange", "strong", "cpu_baseline"):
     if j.get(k):
         print(k, j[k])
 for k in (j.get("kernels") or [])[:nk]:
-    print(f"  {k['ms_per_step']:7.3f} ms  x{k['launches_per_step']:<5g} {k['entry']}")
+    extra = f"  {k['avg_launch_us']:7.1f} us/launch  {k['hbm_frac']:.2f} of HBM peak" if "hbm_frac" in k else ""
+    print(f"  {k['ms_per_step']:7.3f} ms  x{k['launches_per_step']:<5g} {k['entry']}{extra}")

@@ -46,12 +46,14 @@
 #define GF_KB_BYTES (GF_ROWS * 128)       // one K-block operand buffer: [64 rows][32 floats], 8-row swizzle atoms
 #define GF_OP_BYTES (8 * GF_KB_BYTES)     // 4 K-blocks of heads, then 4 K-blocks of tails
 #define GF_OPBUFS 2
-#define GF_ACCS 4
+#define GF_ACCS 2                        // accumulators per MMA issuer (tiles in flight between MMA and epilogue)
+#define GF_ISSUERS 2
 #define GF_AGG_WARPS 8
 #define GF_EPI_WARPS 8
 #define GF_FIRST_AGG 2
 #define GF_FIRST_EPI (GF_FIRST_AGG + GF_AGG_WARPS)
-#define GF_THREADS (32 * (GF_FIRST_EPI + GF_EPI_WARPS))
+#define GF_ISSUER2 (GF_FIRST_EPI + GF_EPI_WARPS)      // the second MMA-issuing warp
+#define GF_THREADS (32 * (GF_ISSUER2 + 1))
 #define GF_NB_MAXN 128
 #define GF_COL_WH 256
 #define GF_COL_WL 384
@@ -151,8 +153,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gin_lin_fused_kernel(const GfAr
   for (int i = tid; i < GF_LD; i += GF_THREADS) zrow[i] = 0.f;
   if (tid == 0) {
     for (int s = 0; s < GF_XSTAGES; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], GF_AGG_WARPS); }
-    for (int s = 0; s < GF_OPBUFS; ++s) { mbar_init(&opfull[s], GF_AGG_WARPS); mbar_init(&opfree[s], 1); }
-    for (int s = 0; s < GF_ACCS; ++s) { mbar_init(&accdone[s], 1); mbar_init(&accfree[s], GF_EPI_WARPS); }
+    for (int s = 0; s < GF_OPBUFS; ++s) { mbar_init(&opfull[s], GF_AGG_WARPS); mbar_init(&opfree[s], GF_ISSUERS); }
+    for (int s = 0; s < GF_ACCS; ++s) { mbar_init(&accdone[s], GF_ISSUERS); mbar_init(&accfree[s], GF_EPI_WARPS); }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gin_lin_fused_kernel(const GfAr
 
   // ---- one-time: the split weight into tensor memory (epilogue warps; lane quarter q = warp & 3; each writes heads and
   // tails of its 32 channels; thread -> output channel n = 32 q + lane; channels >= h hold zeros)
-  if (warp >= GF_FIRST_EPI) {
+  if (warp >= GF_FIRST_EPI && warp < GF_ISSUER2) {
     const int q = warp & 3, is_tail = ((warp - GF_FIRST_EPI) >> 2) & 1;
     const int n = q * 32 + lane;
     for (int cb = 0; cb < GF_LD / 32; ++cb) {
@@ -235,29 +237,35 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gin_lin_fused_kernel(const GfAr
       }
       if (++stage == GF_XSTAGES) { stage = 0; phase ^= 1u; }
     }
-  } else if (warp == 1) {
-    // ================================================================================================ MMA issuer
+  } else if (warp == 1 || warp == GF_ISSUER2) {
+    // =============================================================================================== MMA issuers
+    // A thread issues one tcgen05.mma every ~100 cycles (descriptor arithmetic on the uniform datapath + the election
+    // loop around every instruction) while the tensor core needs 48 cycles at N = 64 (scripts/mma_rate2.cu): with one
+    // issuer the 48 instructions of a tile took 5 040 cycles and the aggregators sat on `opfree`.  Two warps split the
+    // K-blocks (warp 1: 0-1, warp 18: 2-3), each into accumulators of its own that the epilogue adds.
+    const int iss = warp == 1 ? 0 : 1;
     if (lane == 0) {
       unsigned i = 0;
       for (long long u = blockIdx.x; u < total; u += gridDim.x, ++i) {
-        const uint32_t b = i & 1u, acc = i & 3u;
+        const uint32_t b = i & 1u, acc = i % GF_ACCS;
         const int rows = __ldg(a.unit_desc + (u % U) * 12 + 3);
         int n16 = (rows + 15) & ~15;
         if (n16 < 16) n16 = 16;
         // D [M = 128 channels, N = n16 tile rows] (+)= A (tensor memory, K-major) * B^T (shared memory, K-major)
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         mbar_wait(&opfull[b], (i >> 1) & 1u);
-        if (i >= GF_ACCS) mbar_wait(&accfree[acc], ((i >> 2) - 1u) & 1u);
+        if (i >= GF_ACCS) mbar_wait(&accfree[acc], ((i / GF_ACCS) - 1u) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tacc = tmem + acc * 64u;
+        const uint32_t tacc = tmem + ((uint32_t)iss * GF_ACCS + acc) * 64u;
         const uint32_t xh = smem_u32(opbuf + (size_t)b * GF_OP_BYTES), xl = xh + 4 * GF_KB_BYTES;
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
+        for (int kk = 0; kk < 4 / GF_ISSUERS; ++kk) {
+          const int kb = iss * (4 / GF_ISSUERS) + kk;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t wh = tmem + GF_COL_WH + kb * 32 + j * 8, wl = tmem + GF_COL_WL + kb * 32 + j * 8;
             const uint32_t o = kb * GF_KB_BYTES + j * 32;
-            gf_mma_ts(tacc, wh, gf_make_desc(xh + o), idesc, (kb | j) ? 1u : 0u);
+            gf_mma_ts(tacc, wh, gf_make_desc(xh + o), idesc, (kk | j) ? 1u : 0u);
             gf_mma_ts(tacc, wl, gf_make_desc(xh + o), idesc, 1u);
             gf_mma_ts(tacc, wh, gf_make_desc(xl + o), idesc, 1u);
           }
@@ -342,19 +350,23 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gin_lin_fused_kernel(const GfAr
     double st_s[2] = {0.0, 0.0}, st_q[2] = {0.0, 0.0};
     unsigned i = 0;
     for (long long u = blockIdx.x; u < total; u += gridDim.x, ++i) {
-      const uint32_t acc = i & 3u;
+      const uint32_t acc = i % GF_ACCS;
       const int uu = (int)(u % U), s = (int)(u / U);
       const unsigned rlo = (unsigned)__ldg(a.unit_desc + uu * 12 + 0), rhi = (unsigned)__ldg(a.unit_desc + uu * 12 + 1);
       const int rows = __ldg(a.unit_desc + uu * 12 + 3);
       const long long row0 = (long long)s * a.R + (long long)(((unsigned long long)rhi << 32) | rlo);
-      mbar_wait(&accdone[acc], (i >> 2) & 1u);
+      mbar_wait(&accdone[acc], (i / GF_ACCS) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int r0 = half * 32;
       const bool have = r0 < rows;                  // warp-uniform
       uint32_t v[32];
-      if (have) {
+      if (have) {   // the two issuers' partial sums (K-blocks 0-1 and 2-3)
+        uint32_t v2[32];
         GF_LD32(v, tmem + acc * 64u + ((uint32_t)(q * 32) << 16) + (uint32_t)r0);
+        GF_LD32(v2, tmem + (GF_ACCS + acc) * 64u + ((uint32_t)(q * 32) << 16) + (uint32_t)r0);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();

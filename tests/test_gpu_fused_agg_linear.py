@@ -57,10 +57,9 @@ def test_fused_matches_two_kernel_path_bit_for_bit(B, shape, S, h, eps):
          p(sl.unit_desc), p(gi.in_pack), p(gi.in_ptr), p(gi.in_src), sl.R, gi.B, S, 128, sl.tile_rows, 0)
     torch.cuda.synchronize()
     assert torch.equal(A1, A0), f"A differs: max {float((A1 - A0).abs().max()):.3e}"
-    if ref_is_tc:   # same split, same MMA order as linear_tc.cu: bit-identical
-        assert torch.equal(H1, H0), f"H differs: max {float((H1 - H0).abs().max()):.3e} of {float(H0.abs().max()):.3e}"
-    else:
-        assert_close_rel(H1.cpu(), H0.cpu(), 2e-6, what="H vs the FFMA kernel")
+    # same operand split as linear_tc.cu, but the fused kernel's two MMA-issuing warps accumulate K-blocks 0-1 and 2-3
+    # separately (the epilogue adds the two partial sums): equal to fp32 rounding, not bit for bit
+    assert_close_rel(H1.cpu(), H0.cpu(), 2e-6, what="H vs the separate Linear kernel")
     # (both kernels add 32-row partial sums in fp32 before the fp64 accumulation; the 32-row blocks differ)
     assert_close_rel(st1.cpu(), st0.cpu(), 1e-6 if ref_is_tc else 1e-5, floor=float(st0.abs().max()), what="column statistics")
     # and against the oracle's arithmetic in fp64
@@ -117,8 +116,12 @@ def test_phi_stack_same_result_with_and_without_fusion():
             outs[f] = (xr.detach().clone(), [p_.grad.clone() for p_ in phi2.parameters() if p_.grad is not None])
     finally:
         L.sb_set_fused_agg_linear(1 if old != 0 else 0)
-    # A and H are bit-identical; the BatchNorm column sums are accumulated in a different order (1e-8 relative), so
-    # everything downstream agrees to rounding, not bit for bit
-    assert_close_rel(outs[1][0], outs[0][0], 1e-6, what="phi output fused vs unfused")
+    # A is bit-identical, H equal to fp32 rounding (two partial accumulators), the BatchNorm column sums are accumulated
+    # in a different order: everything downstream agrees to rounding - the path's 1e-5 bar - not bit for bit
+    assert_close_rel(outs[1][0], outs[0][0], 1e-5, what="phi output fused vs unfused")
+    # gradients: H now differs in the last bit between the two paths, so pre-activations within rounding distance of a
+    # ReLU kink fall on either side of it - the sensitivity DESIGN.md §2 measures on the fp32 oracle itself (1e-3 from its
+    # own fp64 run at this depth).  The arithmetic proper is pinned at 1e-5 with the ReLU patterns imposed
+    # (tests/test_gpu_signnet.py::test_phi_stack_forward_backward); this A/B check only guards against gross errors.
     for a, b in zip(outs[0][1], outs[1][1]):
-        assert_close_rel(a, b, 1e-5, floor=float(b.abs().max()), what="phi gradients fused vs unfused")
+        assert_close_rel(a, b, 5e-3, floor=float(b.abs().max()), what="phi gradients fused vs unfused")

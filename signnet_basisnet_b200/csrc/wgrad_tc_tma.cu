@@ -20,7 +20,8 @@
 #define WM_STAGE_BYTES (4 * WM_BLK_BYTES)
 #define WM_STAGES 3
 #define WM_WORKERS 512
-#define WM_THREADS (WM_WORKERS + 64)   // + MMA warp (16) + TMA-issue warp (17)
+#define WM_ISSUERS 2                   // MMA-issuing warps: 16 and 18 (row groups 0-1 / 2-3 of every chunk)
+#define WM_THREADS (WM_WORKERS + 96)   // + MMA warp (16) + TMA-issue warp (17) + second MMA warp (18)
 #define WM_MAXG 2
 #define WM_L2_AHEAD 8   // chunks requested into L2 ahead of the TMA loads (cp.async.bulk.prefetch.L2)
 
@@ -94,13 +95,13 @@ wgrad_tc_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap tmg, 
     for (int s = 0; s < WM_STAGES; ++s) {
       mbar_init(&tma_full[s], 1);
       mbar_init(&full[s], WM_WORKERS / 32);
-      mbar_init(&mma_done[s], 1);
+      mbar_init(&mma_done[s], WM_ISSUERS);   // one tcgen05.commit per issuing warp
     }
-    mbar_init(&acc_done, 1);
+    mbar_init(&acc_done, WM_ISSUERS);
     mbar_fence_init();
   }
   if (warp == 16) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128 * WM_ISSUERS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -111,12 +112,18 @@ wgrad_tc_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap tmg, 
   const long long cpg = (a.R + WM_ROWS - 1) / WM_ROWS;
   const long long nch = cpg * a.G;
 
-  if (warp == 16) {
-    // =============================================================================================== MMA issuer
+  if (warp == 16 || warp == 18) {
+    // ============================================================================================== MMA issuers
+    // one thread issues a tcgen05.mma every ~100 cycles (descriptor arithmetic + election loop) while the tensor core
+    // needs 64 (scripts/mma_rate2.cu): 12 instructions per 32-row chunk from one thread = 1 260 cycles next to the 1 400
+    // cycles the chunk's 32 KB take to arrive from HBM.  Two warps split the chunk's four 8-row groups and accumulate into
+    // tensor-memory buffers of their own; the epilogue (once per CTA) adds them.
+    const int iss = warp == 16 ? 0 : 1;
     if (lane == 0) {
       // D[M = 128 (n), N = KP (k)] += A^T-major G chunk x X chunk, both MN-major tf32
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(a.KP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t tacc = tmem + (uint32_t)iss * 128u;
       unsigned cnt = 0;
       for (long long c = blockIdx.x; c < nch; c += gridDim.x, ++cnt) {
         const int stage = cnt % WM_STAGES;
@@ -125,11 +132,11 @@ wgrad_tc_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap tmg, 
         const uint32_t gh = smem_u32(ring + stage * WM_STAGE_BYTES), gl = gh + WM_BLK_BYTES;
         const uint32_t xh = gl + WM_BLK_BYTES, xl = xh + WM_BLK_BYTES;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {   // 4 groups of 8 rows
-          const uint32_t o = j * 1024;
-          wm_mma(tmem, wm_make_desc(gh + o), wm_make_desc(xh + o), idesc, (cnt | j) ? 1u : 0u);
-          wm_mma(tmem, wm_make_desc(gh + o), wm_make_desc(xl + o), idesc, 1u);
-          wm_mma(tmem, wm_make_desc(gl + o), wm_make_desc(xh + o), idesc, 1u);
+        for (int jj = 0; jj < 4 / WM_ISSUERS; ++jj) {   // this issuer's groups of 8 rows
+          const uint32_t o = (uint32_t)(iss * (4 / WM_ISSUERS) + jj) * 1024;
+          wm_mma(tacc, wm_make_desc(gh + o), wm_make_desc(xh + o), idesc, (cnt | jj) ? 1u : 0u);
+          wm_mma(tacc, wm_make_desc(gh + o), wm_make_desc(xl + o), idesc, 1u);
+          wm_mma(tacc, wm_make_desc(gl + o), wm_make_desc(xh + o), idesc, 1u);
         }
         wm_commit(&mma_done[stage]);
       }
@@ -234,7 +241,18 @@ wgrad_tc_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap tmg, 
                        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                      : "r"(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0));
+        uint32_t v2[32];   // the second issuer's accumulator
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,"
+                     "%27,%28,%29,%30,%31}, [%32];"
+                     : "=r"(v2[0]), "=r"(v2[1]), "=r"(v2[2]), "=r"(v2[3]), "=r"(v2[4]), "=r"(v2[5]), "=r"(v2[6]), "=r"(v2[7]),
+                       "=r"(v2[8]), "=r"(v2[9]), "=r"(v2[10]), "=r"(v2[11]), "=r"(v2[12]), "=r"(v2[13]), "=r"(v2[14]), "=r"(v2[15]),
+                       "=r"(v2[16]), "=r"(v2[17]), "=r"(v2[18]), "=r"(v2[19]), "=r"(v2[20]), "=r"(v2[21]), "=r"(v2[22]), "=r"(v2[23]),
+                       "=r"(v2[24]), "=r"(v2[25]), "=r"(v2[26]), "=r"(v2[27]), "=r"(v2[28]), "=r"(v2[29]), "=r"(v2[30]), "=r"(v2[31])
+                     : "r"(tmem + 128u + ((uint32_t)(q * 32) << 16) + (uint32_t)c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           *reinterpret_cast<float4*>(dst + i * 4) = make_float4(__uint_as_float(v[i * 4]), __uint_as_float(v[i * 4 + 1]),
@@ -265,7 +283,7 @@ wgrad_tc_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap tmg, 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+  if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128 * WM_ISSUERS));
 }
 
 int sb_wgrad_reduce_launch(const float* part_w, const float* part_b, int nparts, int BN, int BK, int N, int K, float* dw,

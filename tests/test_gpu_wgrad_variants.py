@@ -1,6 +1,7 @@
 """The two tcgen05 weight-gradient kernels behind sb_linear_wgrad - the TMA-fed wgrad_tc_tma.cu (default for N = K = 128)
 and the register-fed wgrad_tc.cu (every other fast shape; forced everywhere by sb_set_tensor_cores(2)) - against each
-other (bit for bit: same operands, same MMA order, same deterministic reduction) and against an fp64 product."""
+other (same operands and deterministic reduction; the TMA-fed kernel's two MMA-issuing warps keep two partial
+accumulators, so the two agree to fp32 rounding, the bias gradient bit for bit) and against an fp64 product."""
 import pytest
 import torch
 
@@ -49,5 +50,5 @@ def test_wgrad_tma_matches_register_fed(R, pro, bias, G):
         assert_close_rel(out[1][1].cpu(), ref_b.float().cpu(), 1e-5, floor=float(gy.abs().sum((0, 1)).max()),
                          what="dbias")
         assert torch.equal(out[1][1], out[2][1])
-    assert torch.equal(out[1][0], out[2][0])
+    assert_close_rel(out[1][0].cpu(), out[2][0].cpu(), 2e-6, floor=floor, what="TMA-fed vs register-fed")
 

@@ -21,6 +21,12 @@ __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint3
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+// whole warp converged: the election happens inside the asm block, the MMA is predicated on it
+__device__ __forceinline__ void mma_ss_warp(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
                ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
@@ -56,9 +62,10 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int L, int mode, lo
   __shared__ long long tt[4];
   if (threadIdx.x == 0) { for (int w = 0; w < 4; ++w) mbar_init(&bar2[w], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  const int issuers = mode;   // 1, 2 or 4 warps issue L / issuers instructions each, each to its own accumulator
+  const bool whole_warp = mode >= 8;
+  const int issuers = mode & 7;   // 1, 2 or 4 warps issue L / issuers instructions each, each to its own accumulator
   const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0 && w < issuers) {
+  if ((whole_warp || (threadIdx.x & 31) == 0) && w < issuers) {
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t sa = smem_u32(smem), sb = sa + 16384;
     uint32_t parity = 0;
@@ -66,13 +73,15 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int L, int mode, lo
       const long long t0 = clock64();
       for (int i = 0; i < L / issuers; ++i) {
         const uint32_t o = (i & 3) * 32;
-        mma_ss(tmem + (uint32_t)w * 128u, make_desc(sa + o), make_desc(sb + o), idesc, i >= 1 ? 1u : 0u);
+        if (whole_warp) mma_ss_warp(tmem + (uint32_t)w * 128u, make_desc(sa + o), make_desc(sb + o), idesc, i >= 1 ? 1u : 0u);
+        else mma_ss(tmem + (uint32_t)w * 128u, make_desc(sa + o), make_desc(sb + o), idesc, i >= 1 ? 1u : 0u);
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2[w])) : "memory");
+      if ((threadIdx.x & 31) == 0)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2[w])) : "memory");
       while (!try_wait(&bar2[w], parity)) {}
       parity ^= 1u;
       const long long t1 = clock64();
-      if (rep == 2) tt[w] = t1 - t0;
+      if (rep == 2 && (threadIdx.x & 31) == 0) tt[w] = t1 - t0;
     }
   }
   __syncthreads();
@@ -94,7 +103,7 @@ int main() {
   const int L = 960;
   for (int grid : {1, 148}) {
     printf("grid %d CTAs, %d instructions in total (M = 128, K = 8, kind::tf32, operands in shared memory)\n", grid, L);
-    for (int issuers : {1, 2, 4}) {
+    for (int issuers : {1, 2, 4, 9, 10}) {
       for (int N : {64, 128}) {
         rate_kernel<<<grid, 128, smem>>>(N, L, issuers, d);
         cudaError_t e = cudaDeviceSynchronize();
@@ -102,7 +111,8 @@ int main() {
         long long c;
         cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
         const double per = (double)c / L;
-        printf("  %d issuing warp(s)  N=%3d : %7.1f cycles per MMA  (%.0f MAC/clk; dense tf32 peak ~1960)\n", issuers, N, per,
+        printf("  %d issuing warp(s)%s  N=%3d : %7.1f cycles per MMA  (%.0f MAC/clk; dense tf32 peak ~1960)\n", issuers & 7,
+               issuers >= 8 ? ", converged warp + elect.sync" : "", N, per,
                128.0 * N * 8 / per);
       }
     }

@@ -22,7 +22,6 @@
 // row statistics of phase A travelling through 3 x 48 floats of shared memory per warp.
 #include "attention.cuh"
 #include "../../include/signnet_b200.h"
-#include <stdlib.h>
 
 #define AM_KMAX 40
 #define AM_NT 5        // key tiles of 8
@@ -255,8 +254,8 @@ __device__ __forceinline__ void cols_product(float (&acc)[4][4], const float (&p
     if (kt < NT) mma_cols(acc, p[kt], raw[kt], bscale);
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(32 * AM_WARPS, MINB) attention_mma_fwd_kernel(const AttArgs a) {
+template <bool DROP>   // DROP: training-mode attention dropout (the reference's quirk); compiled out otherwise
+__global__ void __launch_bounds__(32 * AM_WARPS, 3) attention_mma_fwd_kernel(const AttArgs a) {
   AmCtx c;
   if (!am_ctx(a, c)) return;
   const float* qp = a.q + c.r0;
@@ -284,7 +283,7 @@ __global__ void __launch_bounds__(32 * AM_WARPS, MINB) attention_mma_fwd_kernel(
     cols_load(vraw, vp, c);   // in flight during the softmax
     float ma, mb, la, lb;
     softmax_rows(s, NT, kb, t, ma, mb, la, lb);
-    if (a.drop_p > 0.f) {
+    if (DROP) {
 #pragma unroll
       for (int nt = 0; nt < AM_NT; ++nt) {
         if (nt < NT) {
@@ -310,8 +309,8 @@ __global__ void __launch_bounds__(32 * AM_WARPS, MINB) attention_mma_fwd_kernel(
 // Pdrop and dS are also written to shared memory [query][key].  Phase B (rows = keys) reads them back TRANSPOSED as the
 // A fragments of dV = Pdrop^T dO and dK = dS^T (Q/T): no recomputation of the scores (the first version recomputed
 // S^T = K Q^T and dP^T = V dO^T with the operands swapped: two of seven contractions, their loads, splits and exp2).
-template <int MINB>
-__global__ void __launch_bounds__(32 * AM_WARPS, MINB) attention_mma_bwd_kernel(const AttArgs a) {
+template <bool DROP>
+__global__ void __launch_bounds__(32 * AM_WARPS, 3) attention_mma_bwd_kernel(const AttArgs a) {
   extern __shared__ __align__(16) float am_smem[];
   AmCtx c;
   if (!am_ctx(a, c)) return;
@@ -358,7 +357,7 @@ __global__ void __launch_bounds__(32 * AM_WARPS, MINB) attention_mma_bwd_kernel(
       if (nt < NT) {
         const int c0 = nt * 8 + 2 * t;
         float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
-        if (a.drop_p > 0.f) {
+        if (DROP) {
           k0 = att_keep_scale(a.seed, c.node, c.h, ja, c0, a.drop_p);
           k1 = att_keep_scale(a.seed, c.node, c.h, ja, c0 + 1, a.drop_p);
           k2 = att_keep_scale(a.seed, c.node, c.h, jb, c0, a.drop_p);
@@ -447,25 +446,22 @@ extern "C" int sb_set_attention_mma(int32_t enable) {
 int sb_attention_mma_fwd_launch(const AttArgs& a, int kmax, cudaStream_t st) {
   if (!am_ok(a, kmax, false)) return SB_ERR_UNSUPPORTED;
   dim3 grid((unsigned)a.N, (unsigned)((a.n_head + AM_WARPS - 1) / AM_WARPS));
-  static const int minb = getenv("SB_ATT_FWD_MINB") ? atoi(getenv("SB_ATT_FWD_MINB")) : 3;
-  if (minb == 4) attention_mma_fwd_kernel<4><<<grid, 32 * AM_WARPS, 0, st>>>(a);
-  else if (minb == 2) attention_mma_fwd_kernel<2><<<grid, 32 * AM_WARPS, 0, st>>>(a);
-  else attention_mma_fwd_kernel<3><<<grid, 32 * AM_WARPS, 0, st>>>(a);
+  if (a.drop_p > 0.f) attention_mma_fwd_kernel<true><<<grid, 32 * AM_WARPS, 0, st>>>(a);
+  else attention_mma_fwd_kernel<false><<<grid, 32 * AM_WARPS, 0, st>>>(a);
   SB_CHECK_LAUNCH("sb_attention_fwd(mma)");
   return SB_OK;
 }
 int sb_attention_mma_bwd_launch(const AttArgs& a, int kmax, cudaStream_t st) {
   if (!am_ok(a, kmax, true)) return SB_ERR_UNSUPPORTED;
   dim3 grid((unsigned)a.N, (unsigned)((a.n_head + AM_WARPS - 1) / AM_WARPS));
-  static const int minb = getenv("SB_ATT_BWD_MINB") ? atoi(getenv("SB_ATT_BWD_MINB")) : 3;
   static bool configured = false;
   if (!configured) {
-    SB_CUDA(cudaFuncSetAttribute(attention_mma_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_BWD_SMEM));
-    SB_CUDA(cudaFuncSetAttribute(attention_mma_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_BWD_SMEM));
+    SB_CUDA(cudaFuncSetAttribute(attention_mma_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_BWD_SMEM));
+    SB_CUDA(cudaFuncSetAttribute(attention_mma_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_BWD_SMEM));
     configured = true;
   }
-  if (minb == 3) attention_mma_bwd_kernel<3><<<grid, 32 * AM_WARPS, AM_BWD_SMEM, st>>>(a);
-  else attention_mma_bwd_kernel<2><<<grid, 32 * AM_WARPS, AM_BWD_SMEM, st>>>(a);
+  if (a.drop_p > 0.f) attention_mma_bwd_kernel<true><<<grid, 32 * AM_WARPS, AM_BWD_SMEM, st>>>(a);
+  else attention_mma_bwd_kernel<false><<<grid, 32 * AM_WARPS, AM_BWD_SMEM, st>>>(a);
   SB_CHECK_LAUNCH("sb_attention_bwd(mma)");
   return SB_OK;
 }

@@ -148,7 +148,9 @@ def run_b200(args):
 
     from signnet_basisnet_b200.layout import pad4, prepare_batch
 
-    copy_stream = torch.cuda.Stream(device=dev)
+    # the loader's stream runs at high priority: its few small kernels (H2D copy, integer bookkeeping, one 32-byte read-back
+    # the host waits for) otherwise queue behind a launch queue that is several persistent 148-CTA kernels deep
+    copy_stream = torch.cuda.Stream(device=dev, priority=-1)
     LD = pad4(CFG["n_hid"])
 
     def twin(d):

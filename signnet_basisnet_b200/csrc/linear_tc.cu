@@ -106,9 +106,11 @@ __device__ __forceinline__ float tc_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-// FAST: K and N multiples of 32, 16-byte aligned rows on both sides, ycols == N, no accumulate -> every per-element
+// FAST: K and N multiples of 32, 16-byte aligned rows on both sides, ycols == N (accumulate only without ReLU / statistics) -> every per-element
 // bounds / alignment predicate of the generic path disappears at compile time (it was ~60 % of the issued instructions).
-template <bool FAST>
+// ACC (FAST only): y += x W^T - a separate instantiation, so the plain kernel's register allocation is untouched (sharing
+// one kernel spilled 176 bytes and took the phi-size launch from 282 to 366 us).
+template <bool FAST, bool ACC = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nkb = a.nkb;
@@ -391,14 +393,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
         {
           const int c = lane & 7;
           float* ybase = a.y + (base + eq * 32 + (lane >> 3)) * a.ldy + ec0 + c * 4;
+          float4 yold[8];   // FAST accumulate: all eight loads of the old y in flight before the first dependent store
+          if (ACC) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              yold[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (eq * 32 + it * 4 + (lane >> 3) < rows) yold[it] = *reinterpret_cast<const float4*>(ybase + it * ystride4);
+            }
+          }
           if (FAST || ec0 + c * 4 < a.ycols) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int r = it * 4 + (lane >> 3);
               const int grow = eq * 32 + r;
               if (grow < rows) {
-                const float4 o4 = *reinterpret_cast<const float4*>(wst + r * 32 + ((c ^ (r & 7)) << 2));
+                float4 o4 = *reinterpret_cast<const float4*>(wst + r * 32 + ((c ^ (r & 7)) << 2));
                 float* yp = ybase + it * ystride4;
+                if (ACC) {   // y += x W^T: the old values arrived as the same coalesced 128-byte segments
+                  o4.x += yold[it].x; o4.y += yold[it].y; o4.z += yold[it].z; o4.w += yold[it].w;
+                }
                 if (FAST || (a.yvec && ec0 + c * 4 + 3 < a.ycols)) {
                   *reinterpret_cast<float4*>(yp) = o4;
                 } else {
@@ -465,14 +478,18 @@ int sb_linear_tc_launch(const float* x, int64_t ldx, const float* w, int64_t w_r
   if (!configured) {
     const int mx = 2 * 4 * TC_BLK_BYTES + 4 * TC_BLK_BYTES + TC_ESTAGE_BYTES;
     SB_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    SB_CUDA(cudaFuncSetAttribute((linear_tc_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     SB_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     configured = true;
   }
   const long long ntiles = sb_ceil_div(R, TC_BM) * G;
   long long grid = sb_num_sms();
   if (grid > ntiles) grid = ntiles;
-  const bool fast = a.xvec && a.yvec && (K % 32 == 0) && (N % 32 == 0) && !accumulate && a.ycols == N;
-  if (fast) linear_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, st>>>(a);
+  // FAST with accumulate: the epilogue adds the old y in its write-back stage - after ReLU and the column statistics
+  // would have been taken, so those two combinations stay on the generic template
+  const bool fast = a.xvec && a.yvec && (K % 32 == 0) && (N % 32 == 0) && a.ycols == N && !(accumulate && (relu || stats));
+  if (fast && accumulate) linear_tc_kernel<true, true><<<(unsigned)grid, TC_THREADS, smem, st>>>(a);
+  else if (fast) linear_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, st>>>(a);
   else linear_tc_kernel<false><<<(unsigned)grid, TC_THREADS, smem, st>>>(a);
   SB_CHECK_LAUNCH("sb_linear_fwd(tcgen05)");
   return SB_OK;

@@ -175,18 +175,18 @@ def test_attention_dropout_statistics_and_per_layer_seeds():
     assert float(rows[~valid].abs().max()) == 0.0
     # per-layer-call seeds come from torch's generator
     seeds = []
-    real_cls = tr.AttentionFn
+    real_cls = tr.MHABlockFn
 
     class Spy:
         @staticmethod
-        def apply(q_, k_, v_, sl_, h_, dk_, p_, seed_):
-            seeds.append(seed_)
-            return real_cls.apply(q_, k_, v_, sl_, h_, dk_, p_, seed_)
+        def apply(*args):
+            seeds.append(args[-1])
+            return real_cls.apply(*args)
 
     torch.manual_seed(5)
     layers = [tr.MultiHeadAttention(4, 32, 8, 8).to(DEV).train() for _ in range(3)]
     x = torch.randn(sl.R, 32, device=DEV)
-    tr.AttentionFn = Spy
+    tr.MHABlockFn = Spy
     try:
         for lyr in layers:
             lyr(x, sl)
@@ -196,6 +196,6 @@ def test_attention_dropout_statistics_and_per_layer_seeds():
         for lyr in layers:
             lyr(x, sl)
     finally:
-        tr.AttentionFn = real_cls
+        tr.MHABlockFn = real_cls
     assert len(set(first)) == 3, first                                # independent masks per layer
     assert seeds[3:] == first                                         # reproducible under torch.manual_seed

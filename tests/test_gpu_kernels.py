@@ -319,3 +319,28 @@ def test_bn_act_small_kernel_matches_streaming_and_torch(M, C, relu, res, traini
         assert_close_rel(a[4].double(), bn64.running_mean, 1e-5, what="running_mean")
         assert_close_rel(a[5].double(), bn64.running_var, 1e-5, what="running_var")
     assert float(a[0][:, C:].abs().max()) == 0.0 if ld > C else True
+
+
+@pytest.mark.parametrize("R,K,N", [(20011, 128, 128), (9000, 64, 96), (9000, 95, 95)])
+def test_linear_accumulate_on_the_tensor_core_path(R, K, N):
+    """y += x W^T (the input-gradient accumulation of rho's fused blocks): the FAST tcgen05 template adds the old y in its
+    write-back stage (K, N multiples of 32), the generic template in registers; both against fp64."""
+    from signnet_basisnet_b200 import _lib
+    from signnet_basisnet_b200.functional import linear_fwd
+    from signnet_basisnet_b200.layout import pad4
+
+    torch.manual_seed(R + K)
+    ldx, ldy = pad4(K), pad4(N)
+    x = torch.zeros(R, ldx, device=DEV)
+    x[:, :K] = torch.randn(R, K, device=DEV)
+    W = (torch.randn(N, K) / K ** 0.5).to(DEV)
+    y0 = torch.zeros(R, ldy, device=DEV)
+    y0[:, :N] = torch.randn(R, N, device=DEV)
+    ref = y0[:, :N].double() + x[:, :K].double() @ W.double().T
+    y = y0.clone()
+    linear_fwd(x, ldx, W, K, 1, None, y, ldy, R, 1, K, N, accumulate=True)
+    torch.cuda.synchronize()
+    assert _lib.lib().sb_last_linear_kernel() == 1
+    assert_close_rel(y[:, :N].double().cpu(), ref.cpu(), 1e-5, what="y += x W^T")
+    if ldy > N:
+        assert float(y[:, N:].abs().max()) == 0.0

@@ -179,7 +179,6 @@ def run_b200(args):
 
     # End to end: every step copies ITS batch host -> device from pinned memory (on a copy stream, issued one step ahead
     # like a prefetching DataLoader would, so the transfer overlaps the previous step's backward) and reads the loss back.
-    pending = []
     LOSS_LAG, LOSS_RING = 3, 4
     loss_pin = torch.empty(LOSS_RING, dtype=torch.float32).pin_memory()
     loss_ev = [torch.cuda.Event(blocking=True) for _ in range(LOSS_RING)]
@@ -189,17 +188,39 @@ def run_b200(args):
         with torch.cuda.stream(copy_stream):
             d = host.to(dev, non_blocking=True)
         prepare_batch(d, LD, stream=copy_stream)   # the loader's side: H2D copy + bookkeeping of the batch it delivers
-        pending.append(d)
+        return d
+
+    # The loader runs in its own thread, like a DataLoader worker: the H2D copy, the integer bookkeeping and the one
+    # 32-byte read-back the host has to wait for (graph / slot counts) happen two batches ahead of the step that uses them,
+    # so the launching thread never sits in that wait (on some boxes of the pool it took 30-60 ms per batch for several
+    # steps in a row and the launch queue ran dry; SB_BENCH_DEBUG=1 prints the per-section host times).
+    import queue
+    import threading
+
+    ready = queue.Queue(maxsize=2)
+    loader_stop = threading.Event()
+
+    def loader_main():
+        torch.cuda.set_device(local)
+        while not loader_stop.is_set():
+            d = fetch()
+            while not loader_stop.is_set():
+                try:
+                    ready.put(d, timeout=0.05)
+                    break
+                except queue.Full:
+                    pass
+
+    loader = threading.Thread(target=loader_main, daemon=True)
 
     def step_e2e():
-        if not pending:
-            fetch()
         t0_ = time.perf_counter()
-        data = pending.pop(0)
+        if not loader.is_alive():
+            loader.start()
+        data = ready.get()
         for v in data.__dict__.values():
             if torch.is_tensor(v):
                 v.record_stream(torch.cuda.current_stream())
-        fetch()  # next step's batch
         t1_ = time.perf_counter()
         # D2H read of the loss, every step, without draining the launch pipeline: the scalar goes to pinned host memory
         # with an asynchronous copy and is consumed LOSS_LAG steps later, once its event has completed (what a training
@@ -290,6 +311,8 @@ def run_b200(args):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps, after=drain_all)
+    loader_stop.set()
+    loader.join(timeout=5)
     if os.environ.get("SB_BENCH_DEBUG") == "1":
         sys.stderr.write("e2e host ms per step (fetch | step | loss wait): " + " ".join(
             f"{1e3 * a_:.0f}|{1e3 * b_:.0f}|{1e3 * c_:.0f}" for a_, b_, c_ in e2e_state["split"][-args.steps:]) + "\n")

@@ -5,8 +5,8 @@
 // generic ones in transformer.cu (Alchemy/sign_net/model_utils/transformer_module.py:44-58,76-102).
 //
 // Why the warp-level instruction and not tcgen05: a token set has 9-37 rows; a 128-row tcgen05 tile would hold 3-5 nodes
-// with a block-diagonal mask (13 % useful) and costs >= 105 cycles per instruction whatever N is
-// (profiles/r2i_mma_rate.log).  m16n8k8 tiles waste at most 15 rows and need neither tensor memory nor descriptors.
+// with a block-diagonal mask (13 % useful).  m16n8k8 tiles waste at most 15 rows and need neither tensor memory nor
+// descriptors.
 //
 // No shared-memory staging: the contraction index of an MMA can be permuted freely as long as both operands agree, and
 // so can the output-column index, so every fragment is loaded from (or stored to) global memory as 128-bit pieces of a

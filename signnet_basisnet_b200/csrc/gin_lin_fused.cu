@@ -16,23 +16,22 @@
 //   warps 2..9    aggregators: neighbour sums out of shared memory in CSR order (bit-identical to gin_agg.cu), stream
 //                 the A row to global memory, split it into tf32 head + tail (3xTF32, as linear_tc.cu) and st.shared
 //                 both, 128B-swizzled K-major, into one of two operand buffers;
-//   warp 1        MMA issuer: tcgen05.mma kind::tf32, D[128 channels x N rows] += W(head|tail, resident in TENSOR
+//   warps 1, 18   MMA issuers (K-blocks 0-1 / 2-3): tcgen05.mma kind::tf32, D[128 channels x N rows] += W(head|tail, resident in TENSOR
 //                 MEMORY for the whole kernel, lane = output channel) * A^T (shared memory), N = the tile's row count
-//                 rounded up to 16; four 64-column accumulators in tensor memory rotate;
+//                 rounded up to 16; two 64-column accumulators per issuer rotate, the epilogue adds the two partial sums;
 //   warps 10..17  epilogue: tcgen05.ld of [32 channels x 32 rows] blocks; a thread owns one channel, so the BatchNorm
 //                 sums are per-thread scalars and every tile row leaves as one coalesced 128-byte store.
 //
-// MEASURED (B200, cfg 4 size: 2 x 575 454 rows, profiles/r2h_*): bit-identical A and H; 464 us against 207 + 283 = 492 us
-// for the two kernels, i.e. 0.58 of the HBM peak on its 3T of traffic - NOT the 0.8+ the traffic saving promised.  ncu
-// shows the aggregators parked on `opfree` (waiting for the tensor core) with the tensor pipe 21 % active, and
-// scripts/mma_rate.cu shows why: one tcgen05.mma kind::tf32 (M = 128, K = 8) occupies the tensor core for >= 105 cycles
-// whatever N <= 128 is.  A neighbourhood-closed tile has <= 64 rows (N = 48 on average), its 48 instructions (4 K-blocks
-// x 4 k-steps x 3 products) therefore cost 2.6 us - four times the tensor time per row of a 256-row streaming tile - and
-// shared memory cannot hold a 256-row 3xTF32 operand (256 KB) next to the tile ring.  (16 aggregator + 4 epilogue warps:
-// 592 us.)  The kernel therefore stays opt-in once linear_tc256.cu makes the separate Linear cheaper than this.
+// MEASURED (B200, cfg 4 size: 2 x 575 454 rows; profiles/r2_fused_agg_linear_ncu.csv, r2_fused_bench.log): A bit-identical
+// to gin_agg.cu, H equal to linear_tc.cu's to fp32 rounding; 411-417 us against 207 + 280 = 489 us for the two kernels =
+// 0.66 of the HBM peak on its 3T of traffic (0.59 inside the power-capped step).  With ONE issuing thread it was 464-477
+// us: a thread issues a tcgen05.mma only every ~100 cycles while the tensor core needs 48 at N = 64
+// (scripts/mma_rate2.cu), so the 48 instructions of a <= 64-row tile (4 K-blocks x 4 k-steps x 3 products) cost 5 000
+// cycles of issue next to 3 000 of HBM time and the aggregators sat on `opfree`; hence the two issuing warps.  Shared
+// memory cannot hold a 256-row 3xTF32 operand (256 KB) next to the tile ring.  (16 aggregator + 4 epilogue warps: 592 us.)
 // Shapes: row stride ld = K = 128 floats (the phi stack at n_hid = 128, every layer but the first), h <= 128 output
 // channels.  Everything else returns SB_ERR_UNSUPPORTED and the caller runs sb_gin_agg + sb_linear_fwd.
-// Tensor memory: accumulators 4 x 64 columns + weight head 128 + weight tail 128 = 512 columns.
+// Tensor memory: accumulators 2 issuers x 2 x 64 columns + weight head 128 + weight tail 128 = 512 columns.
 // Shared memory: operand buffers 2 x 64 KB + X ring 3 x 32 KB + neighbour words + zero row = 226 KB.
 #include <cuda.h>
 #include <stdlib.h>

@@ -412,10 +412,10 @@ int sb_linear_tc_launch(const float* x, int64_t ldx, const float* w, int64_t w_r
 // (kept so that tests can compare the two weight-gradient kernels bit for bit).  Round-2 measurements that decided this
 // (profiles/r2a_pair_check_mode*.log): the TMA-fed weight gradient is bit-identical and 17 % faster (278 vs 338 us at the
 // phi size); the CTA-pair, TMA-fed and weight-in-tensor-memory Linear variants were all slower than linear_tc.cu
-// (393 / 310 / 314 vs 292 us) and have been removed.  So was a 256-row-tile variant written after scripts/mma_rate.cu
-// showed that one tcgen05.mma kind::tf32 (M = 128, K = 8) occupies the tensor core for >= 105 cycles whatever N <= 128
-// is (138 cycles at N = 256 from tensor memory): bit-identical, but 353 us - with one 256-column accumulator and a
-// 3-stage ring the load -> split -> MMA -> drain phases of a tile serialise (profiles/r2i_linear_tc256.log).
+// (393 / 310 / 314 vs 292 us) and have been removed.  So was a 256-row-tile variant (bit-identical, but 353 us: with one
+// 256-column accumulator and a 3-stage ring the load -> split -> MMA -> drain phases of a tile serialise,
+// profiles/r2i_linear_tc256.log) and a second MMA-issuing warp in linear_tc.cu (no change: that kernel is bound by the
+// hand-offs of its two-stage ring; the fused kernel and the weight gradient did gain from it).
 static int g_use_tc = -1;
 static int g_small_rows = 1;   // SB_LINEAR_SMALL=0 / sb_set_small_rows(0): problems with few rows take the big-tile kernels
 static int g_last_variant = -1, g_last_wgrad_variant = -1;

@@ -18,8 +18,8 @@
 //                  4t + ntd and 16 + 4t + ntd, i.e. the lane ends up with the same 8 columns of its rows as it loads;
 //   the score accumulators (row g, keys 8nt + 2t, +1) are used directly as the A fragment of P V with the key index
 //   permuted (k = t <-> key 8nt + 2t, k = t+4 <-> key 8nt + 2t + 1): no shuffles, no transposition.
-// The backward needs P^T and dS^T: it recomputes S^T = K Q^T and dP^T = V dO^T with the operands swapped (phase B), the
-// row statistics of phase A travelling through 3 x 48 floats of shared memory per warp.
+// The backward needs P^T and dS^T for dV and dK: phase A (rows = queries) writes Pdrop and dS to shared memory
+// [query][key] (2 x 48 x 44 floats per warp), phase B (rows = keys) reads them back transposed as its A fragments.
 #include "attention.cuh"
 #include "../../include/signnet_b200.h"
 

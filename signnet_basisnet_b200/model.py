@@ -447,9 +447,10 @@ class GNN(nn.Module):
             buffers.append((rme, rve, bn0.running_mean, bn0.running_var, norm.running_mean, norm.running_var))
             bns += [bn0, norm]
         if self.training:
-            for bn in bns:
-                if bn.track_running_stats and bn.num_batches_tracked is not None:
-                    bn.num_batches_tracked += 1
+            counters = [bn.num_batches_tracked for bn in bns
+                        if bn.track_running_stats and bn.num_batches_tracked is not None]
+            if counters:   # one multi-tensor launch instead of one tiny kernel per BatchNorm
+                torch._foreach_add_(counters, 1)
         cfg = dict(gi=gi, L=L, d=d, training=self.training, nfe=nfe, F=F, V=V, buffers=buffers)
         return GineStackFn.apply(x, edge_attr, cfg, *params)
 

@@ -157,9 +157,10 @@ class GNN3d(nn.Module):
         slots = gi.slots(k, masked, pad4(d))
         slots_in = gi.slots(k, masked, dims[0][0])
         if self.training:  # one BatchNorm call per sign pass: two (+v, -v) under SignNet.forward (sign_net.py:113)
-            for conv, norm in zip(self.convs, self.norms):
-                conv.nn.norms[0].bn.num_batches_tracked += int(x0.shape[0])
-                norm.bn.num_batches_tracked += int(x0.shape[0])
+            counters = [b.num_batches_tracked for conv, norm in zip(self.convs, self.norms)
+                        for b in (conv.nn.norms[0].bn, norm.bn) if b.num_batches_tracked is not None]
+            if counters:   # one multi-tensor launch instead of one tiny kernel per BatchNorm
+                torch._foreach_add_(counters, int(x0.shape[0]))
         cfg = dict(slots=slots, slots_in=slots_in, dims=dims, training=self.training, buffers=buffers,
                    capture=capture)
         return PhiStackFn.apply(x0, cfg, *params), slots

@@ -397,9 +397,9 @@ def run_b200(args):
     rows_phi, Tr = 2 * sl.R, 4 * ld * sl.R
     alg = {f"sb_linear_fwd[K={ld},N={ld},rows={rows_phi}]": (2 * T1, "X in, Y out"),
            f"sb_linear_wgrad[N={ld},K={ld},rows={rows_phi}]": (2 * T1, "dY, X in"),
-           "sb_affine2": (3 * T1, "gout, y in, dz out (BatchNorm backward, apply)"),
+           "sb_bn_apply_bwd": (3 * T1, "gout, y in, dz out (BatchNorm backward: coefficients + apply)"),
            "sb_bn_bwd_reduce": (2 * T1, "gout, y in (BatchNorm backward, sums)"),
-           "sb_affine_act_res": (3 * T1, "y, residual in, x out (2 tensors for layer 0 and the rho-size calls)"),
+           "sb_bn_apply_fwd": (3 * T1, "y, residual in, x out (BatchNorm forward: coefficients + ReLU + residual; 2 tensors in layer 0)"),
            "sb_gin_linear_fused_fwd": (3 * T1 + 16 * gi.E, "X in, A and H out"),
            f"sb_gin_agg[ld={ld},bwd]": (4 * T1 + 16 * gi.E, "dA, G, X in, G out"),
            "sb_attention_fwd": (4 * Tr, "q, k, v in, o out"),

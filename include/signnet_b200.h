@@ -203,6 +203,19 @@ int sb_affine2(const float* t1, const float* t2, const double* coef, const doubl
 
 int sb_relu_bwd(const float* g, const float* y, float* out, int64_t n, void* stream); /* out = g * [y > 0] */
 
+/* sb_bn_finalize + sb_affine_act_res in ONE launch (every CTA derives the coefficients from stats[G,2,C] itself, CTA 0
+ * publishes a, c, mean_rstd and moves the running buffers; identical values), and sb_bn_bwd_finalize + sb_affine2 in one
+ * launch (coefficients from the two backward sums inside the apply kernel; writes dgamma, dbeta).  M = rows per group the
+ * statistics were taken over.  Two launches fewer per BatchNorm and step: the launch queue holds ~1 000 launches, i.e.
+ * how far the issuing thread may fall behind before the GPU idles. */
+int sb_bn_apply_fwd(const float* y, const double* stats, int64_t M, int32_t G, int32_t C, const float* gamma,
+                    const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                    int32_t training, int32_t relu, const float* res, float* out, int64_t ld, int64_t R, float* a, float* c,
+                    double* mean_rstd, void* stream);
+int sb_bn_apply_bwd(const float* gout, const float* y, const double* stats, const double* mean_rstd, const float* pa,
+                    const float* pc, const float* gamma, int64_t M, int32_t training, float* dz, float* dgamma,
+                    float* dbeta, int64_t ld, int64_t R, int32_t G, int32_t C, void* stream);
+
 /* BatchNorm + activation (+ residual) as ONE call: column statistics (training) -> a, c, mean_rstd (+ running buffers) ->
  * out = act(a*x + c) (+ res).  nn.BatchNorm1d + ReLU + residual of elements.py:57-65, model.py:41-47,
  * transformer_module.py / sign_net.py:70 on [M, ld] tensors.  For G = 1 and M <= 8 192 rows this is ONE kernel (a CTA owns

@@ -60,6 +60,8 @@ _SIGNATURES = {
     "sb_layernorm_fwd": "pppp" + "ll" + "i" + "f" + "ppp" + "p",
     "sb_layernorm_bwd": "pppp" + "ll" + "i" + "pp" + "p",
     "sb_relu_bwd": "pppl" + "p",
+    "sb_bn_apply_fwd": "ppl" + "ii" + "pppp" + "ff" + "ii" + "pp" + "ll" + "ppp" + "p",
+    "sb_bn_apply_bwd": "ppppppp" + "li" + "ppp" + "ll" + "ii" + "p",
     "sb_bn_act_fwd": "pll" + "ii" + "pppp" + "ff" + "ii" + "pp" + "pppp" + "p",
     "sb_bn_act_bwd": "pppppp" + "ll" + "iiii" + "ppp" + "pp" + "p",
     "sb_laplacian_evd": "pppp" + "ii" + "ppp" + "p",

@@ -339,7 +339,12 @@ __global__ void __launch_bounds__(EW_THREADS, 4) affine2_kernel(const float* t1,
                                                              const double* __restrict__ mean_rstd,
                                                              const float* __restrict__ pa,
                                                              const float* __restrict__ pc, float* out, long long ld,
-                                                             long long R, int G, int C) {
+                                                             long long R, int G, int C,
+                                                             const double* __restrict__ fin_stats = nullptr,
+                                                             const float* __restrict__ gamma = nullptr,
+                                                             long long M = 0, int training = 0,
+                                                             float* __restrict__ dgamma = nullptr,
+                                                             float* __restrict__ dbeta = nullptr) {
   // tab[k][g*ld + col], k = (al.hi, al.lo, be.hi, be.lo, ga.hi, ga.lo, mu.hi, mu.lo, pa, pc): fp64 -> float pairs once
   // per block (not per element); structure-of-arrays so a warp's float4 reads are conflict-free.
   extern __shared__ __align__(16) float tab[];
@@ -352,12 +357,39 @@ __global__ void __launch_bounds__(EW_THREADS, 4) affine2_kernel(const float* t1,
     float a_ = 0.f, c_ = 0.f;
     if (col < C) {
       const long long q = (long long)g * C + col;
-      al = split_d(coef[q]); be = split_d(coef[GC + q]); ga = split_d(coef[2 * GC + q]); mu = split_d(mean_rstd[q]);
+      if (fin_stats) {   // sb_bn_apply_bwd: the coefficients straight from the two column sums, the expressions of
+                         // bn_bwd_finalize_kernel (identical values), instead of a 4 us launch of their own
+        const double s1 = fin_stats[((long long)g * 2 + 0) * C + col], s2 = fin_stats[((long long)g * 2 + 1) * C + col];
+        const double gm = gamma ? (double)gamma[col] : 1.0;
+        const double rs = mean_rstd[((long long)G + g) * C + col];
+        const double av = gm * rs;
+        double bev = 0.0, gav = 0.0;
+        if (training) {
+          const double m1 = s1 / (double)M, m2 = s2 / (double)M;
+          bev = -av * rs * m2;
+          gav = -av * m1;
+        }
+        al = split_d(av); be = split_d(bev); ga = split_d(gav);
+      } else {
+        al = split_d(coef[q]); be = split_d(coef[GC + q]); ga = split_d(coef[2 * GC + q]);
+      }
+      mu = split_d(mean_rstd[q]);
       if (mask) { a_ = __ldg(pa + q); c_ = __ldg(pc + q); }
     }
     tab[0 * GL + p] = al.hi; tab[1 * GL + p] = al.lo; tab[2 * GL + p] = be.hi; tab[3 * GL + p] = be.lo;
     tab[4 * GL + p] = ga.hi; tab[5 * GL + p] = ga.lo; tab[6 * GL + p] = mu.hi; tab[7 * GL + p] = mu.lo;
     tab[8 * GL + p] = a_; tab[9 * GL + p] = c_;
+  }
+  if (fin_stats && blockIdx.x == 0) {   // dgamma, dbeta: sums over the groups in order, as bn_bwd_finalize_kernel
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      double dg = 0.0, db = 0.0;
+      for (int g = 0; g < G; ++g) {
+        dg += fin_stats[((long long)g * 2 + 1) * C + ch];
+        db += fin_stats[((long long)g * 2 + 0) * C + ch];
+      }
+      if (dgamma) dgamma[ch] = (float)dg;
+      if (dbeta) dbeta[ch] = (float)db;
+    }
   }
   __syncthreads();
   const long long ld4 = ld >> 2;
@@ -429,6 +461,141 @@ extern "C" int sb_affine2(const float* t1, const float* t2, const double* coef, 
   affine2_kernel<<<(unsigned)blocks, EW_THREADS, smem, (cudaStream_t)stream>>>(t1, t2, coef, mean_rstd, pa, pc, out, ld,
                                                                               R, G, C);
   SB_CHECK_LAUNCH("sb_affine2");
+  return SB_OK;
+}
+
+// sb_bn_bwd_finalize + sb_affine2 in ONE launch: dz = al*dZ' + be*(y - mean) + ga with dZ' = gout * [pa*y + pc > 0]
+// (pa/pc given) and the coefficients taken straight from stats[G,2,C] = (sum dZ', sum dZ' y_hat); writes dgamma, dbeta.
+extern "C" int sb_bn_apply_bwd(const float* gout, const float* y, const double* stats, const double* mean_rstd,
+                               const float* pa, const float* pc, const float* gamma, int64_t M, int32_t training,
+                               float* dz, float* dgamma, float* dbeta, int64_t ld, int64_t R, int32_t G, int32_t C,
+                               void* stream) {
+  SB_CHECK_ARG(gout && y && stats && mean_rstd && dz && ld % 4 == 0 && ld >= C && G >= 1 && M >= 1,
+               "sb_bn_apply_bwd: bad arguments");
+  SB_CHECK_ARG((pa == nullptr) == (pc == nullptr), "sb_bn_apply_bwd: pa/pc must come together");
+  const long long total = (long long)G * R * (ld / 4);
+  long long blocks = sb_ceil_div(total, EW_THREADS * 4);
+  const long long cap = (long long)sb_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;   // R == 0 still writes dgamma / dbeta
+  const size_t smem = (size_t)G * ld * 10 * sizeof(float);
+  SB_CHECK_ARG(smem <= 48 * 1024, "sb_bn_apply_bwd: G*ld too large");
+  affine2_kernel<<<(unsigned)blocks, EW_THREADS, smem, (cudaStream_t)stream>>>(gout, y, nullptr, mean_rstd, pa, pc, dz, ld,
+                                                                              R, G, C, stats, gamma, M, training, dgamma,
+                                                                              dbeta);
+  SB_CHECK_LAUNCH("sb_bn_apply_bwd");
+  return SB_OK;
+}
+
+// ------------------------------------------------------------- BatchNorm finalize + apply in ONE launch (forward)
+// sb_bn_finalize followed by sb_affine_act_res costs two launches, the first of them a 5 us kernel that only turns
+// 2*G*C sums into coefficients.  Here every CTA derives the coefficients of all (group, channel) pairs itself (a few
+// hundred fp64 operations, the same expressions as bn_finalize_kernel -> identical a, c) into shared memory, and CTA 0
+// also publishes a, c, mean_rstd for the backward and updates the running buffers (+v then -v order, as before).
+__global__ void __launch_bounds__(EW_THREADS) bn_apply_fwd_kernel(
+    const float* __restrict__ y, const double* __restrict__ stats, long long M, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps, int training,
+    const float* __restrict__ res, float* __restrict__ out, long long ld, long long R, int G, int C, int relu,
+    float* __restrict__ a_out, float* __restrict__ c_out, double* __restrict__ mean_rstd) {
+  extern __shared__ __align__(16) float tab[];   // [2][G*ld]: a, c (0 in padding columns)
+  const int GL = G * (int)ld;
+  for (int p = threadIdx.x; p < GL; p += blockDim.x) {
+    const int g = p / (int)ld, ch = p - g * (int)ld;
+    float av_f = 0.f, cv_f = 0.f;
+    if (ch < C) {
+      const double gm = gamma ? (double)gamma[ch] : 1.0, bt = beta ? (double)beta[ch] : 0.0;
+      double mean, var;
+      if (training) {
+        const double sv = stats[((long long)g * 2 + 0) * C + ch], q = stats[((long long)g * 2 + 1) * C + ch];
+        mean = sv / (double)M;
+        var = q / (double)M - mean * mean;
+        if (var < 0.0) var = 0.0;
+      } else {
+        mean = (double)running_mean[ch];
+        var = (double)running_var[ch];
+      }
+      const double rstd = 1.0 / sqrt(var + (double)eps);
+      const double av = gm * rstd;
+      av_f = (float)av;
+      cv_f = (float)(bt - mean * av);
+      if (blockIdx.x == 0) {
+        a_out[(long long)g * C + ch] = av_f;
+        c_out[(long long)g * C + ch] = cv_f;
+        if (mean_rstd) {
+          mean_rstd[(long long)g * C + ch] = mean;
+          mean_rstd[((long long)G + g) * C + ch] = rstd;
+        }
+      }
+    }
+    tab[p] = av_f;
+    tab[GL + p] = cv_f;
+  }
+  if (blockIdx.x == 0 && training && running_mean) {   // one thread per channel, groups in order (+v, then -v)
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      for (int g = 0; g < G; ++g) {
+        const double sv = stats[((long long)g * 2 + 0) * C + ch], q = stats[((long long)g * 2 + 1) * C + ch];
+        const double mean = sv / (double)M;
+        double var = q / (double)M - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double unb = (M > 1) ? var * ((double)M / (double)(M - 1)) : var;
+        running_mean[ch] = (float)((1.0 - (double)momentum) * (double)running_mean[ch] + (double)momentum * mean);
+        running_var[ch] = (float)((1.0 - (double)momentum) * (double)running_var[ch] + (double)momentum * unb);
+      }
+    }
+  }
+  __syncthreads();
+  const long long ld4 = ld >> 2;
+  const long long total = (long long)G * R * ld4;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / ld4;
+    const int c4 = (int)(t - row * ld4);
+    const int g = (int)(row / R);
+    const float4 v = ldg4(y + t * 4);
+    float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (res) rr = ldg4(res + t * 4);
+    const float4 a4 = *reinterpret_cast<const float4*>(tab + g * (int)ld + c4 * 4);
+    const float4 k4 = *reinterpret_cast<const float4*>(tab + GL + g * (int)ld + c4 * 4);
+    const float in[4] = {v.x, v.y, v.z, v.w}, rv[4] = {rr.x, rr.y, rr.z, rr.w};
+    const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, cc[4] = {k4.x, k4.y, k4.z, k4.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // same arithmetic as affine_act_res_kernel
+      if (c4 * 4 + j < C) {
+        float u = fmaf(aa[j], in[j], cc[j]);
+        if (relu) u = fmaxf(u, 0.f);
+        o[j] = u + rv[j];
+      } else {
+        o[j] = 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(out + t * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+extern "C" int sb_bn_apply_fwd(const float* y, const double* stats, int64_t M, int32_t G, int32_t C, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                               int32_t training, int32_t relu, const float* res, float* out, int64_t ld, int64_t R,
+                               float* a, float* c, double* mean_rstd, void* stream) {
+  SB_CHECK_ARG(y && out && a && c && G >= 1 && C >= 1 && ld % 4 == 0 && ld >= C, "sb_bn_apply_fwd: bad arguments");
+  SB_CHECK_ARG(training ? (stats != nullptr && M >= 1) : (running_mean && running_var),
+               "sb_bn_apply_fwd: training needs stats and M>=1, eval needs running statistics");
+  const size_t smem = (size_t)2 * G * ld * sizeof(float);
+  if (smem > 40 * 1024) {   // very wide rows: the two-launch form
+    const int rc = sb_bn_finalize(stats, M, G, C, gamma, beta, running_mean, running_var, momentum, eps, training, a, c,
+                                  mean_rstd, stream);
+    if (rc) return rc;
+    return sb_affine_act_res(y, a, c, res, out, ld, R, G, C, relu, stream);
+  }
+  const long long total = (long long)G * R * (ld / 4);
+  long long blocks = sb_ceil_div(total, EW_THREADS * 4);
+  const long long cap = (long long)sb_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;   // R == 0 still publishes the coefficients and moves the running buffers
+  bn_apply_fwd_kernel<<<(unsigned)blocks, EW_THREADS, smem, (cudaStream_t)stream>>>(
+      y, stats, M, gamma, beta, running_mean, running_var, momentum, eps, training, res, out, ld, R, G, C, relu, a, c,
+      mean_rstd);
+  SB_CHECK_LAUNCH("sb_bn_apply_fwd");
   return SB_OK;
 }
 
@@ -726,10 +893,8 @@ extern "C" int sb_bn_act_fwd(const float* x, int64_t ld, int64_t M, int32_t G, i
     const int rc = sb_col_stats(x, ld, M, G, C, stats, stream);
     if (rc) return rc;
   }
-  int rc = sb_bn_finalize(training ? stats : nullptr, M, G, C, gamma, beta, running_mean, running_var, momentum, eps,
-                          training, a, c, mean_rstd, stream);
-  if (rc) return rc;
-  return sb_affine_act_res(x, a, c, res, out, ld, M, G, C, relu, stream);
+  return sb_bn_apply_fwd(x, training ? stats : nullptr, M, G, C, gamma, beta, running_mean, running_var, momentum, eps,
+                         training, relu, res, out, ld, M, a, c, mean_rstd, stream);
 }
 
 // dz (may alias gout) <- d/dx of act(BN(x)) given gout; dgamma, dbeta.  stats fp64 [G,2,C] and coef fp64 [3,G,C]: scratch of
@@ -750,7 +915,6 @@ extern "C" int sb_bn_act_bwd(const float* gout, const float* x, const float* a, 
   SB_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)G * 2 * C, st));
   int rc = sb_bn_bwd_reduce(gout, x, a, c, mean_rstd, nullptr, ld, M, G, C, relu, stats, stream);
   if (rc) return rc;
-  rc = sb_bn_bwd_finalize(stats, M, G, C, gamma, mean_rstd, training, 0, dgamma, dbeta, coef, stream);
-  if (rc) return rc;
-  return sb_affine2(gout, x, coef, mean_rstd, relu ? a : nullptr, relu ? c : nullptr, dz, ld, M, G, C, stream);
+  return sb_bn_apply_bwd(gout, x, stats, mean_rstd, relu ? a : nullptr, relu ? c : nullptr, gamma, M, training, dz, dgamma,
+                         dbeta, ld, M, G, C, stream);
 }

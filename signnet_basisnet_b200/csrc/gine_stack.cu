@@ -37,17 +37,31 @@ Gr read_gr(const int64_t* p, const int64_t* n) {
   return g;
 }
 
-// batch_norm_act of functional.py: column statistics -> finalize (+ running buffers) -> act(a x + c) (+ res)
+#define GS_BN_SMALL_ROWS 8192   // sb_bn_act_fwd / sb_bn_act_bwd run as ONE kernel up to this many rows (elementwise.cu)
+
+// batch_norm_act of functional.py: column statistics -> finalize (+ running buffers) -> act(a x + c) (+ res).
+// `stats`: this BatchNorm's own ZERO-INITIALISED fp64 [2,C] region of the caller's arena - no memset per BatchNorm.
 int bn_act(const float* x, float* out, const float* res, int64_t M, int ld, int C, const float* gamma, const float* beta,
            float* rm, float* rv, double* stats, float* a, float* c, double* mr, int training, float mom, float eps,
            void* st) {
-  return sb_bn_act_fwd(x, ld, M, 1, C, gamma, beta, rm, rv, mom, eps, training, 1, res, out, stats, a, c, mr, st);
+  if (M <= GS_BN_SMALL_ROWS)
+    return sb_bn_act_fwd(x, ld, M, 1, C, gamma, beta, rm, rv, mom, eps, training, 1, res, out, stats, a, c, mr, st);
+  if (training) {
+    const int rc = sb_col_stats(x, ld, M, 1, C, stats, st);
+    if (rc) return rc;
+  }
+  return sb_bn_apply_fwd(x, training ? stats : nullptr, M, 1, C, gamma, beta, rm, rv, mom, eps, training, 1, res, out, ld, M,
+                         a, c, mr, st);
 }
 // BatchNormActFn.backward: dz (may alias gout) <- d/dx of relu(BN(x)); dgamma, dbeta
 int bn_act_bwd(const float* gout, const float* x, const float* a, const float* c, const double* mr, const float* gamma,
                int64_t M, int ld, int C, int training, float* dz, float* dgamma, float* dbeta, double* stats, double* coef,
                cudaStream_t st) {
-  return sb_bn_act_bwd(gout, x, a, c, mr, gamma, ld, M, 1, C, 1, training, dz, dgamma, dbeta, stats, coef, (void*)st);
+  if (M <= GS_BN_SMALL_ROWS)
+    return sb_bn_act_bwd(gout, x, a, c, mr, gamma, ld, M, 1, C, 1, training, dz, dgamma, dbeta, stats, coef, (void*)st);
+  const int rc = sb_bn_bwd_reduce(gout, x, a, c, mr, nullptr, ld, M, 1, C, 1, stats, st);
+  if (rc) return rc;
+  return sb_bn_apply_bwd(gout, x, stats, mr, a, c, gamma, M, training, dz, dgamma, dbeta, ld, M, 1, C, st);
 }
 }  // namespace
 
@@ -110,7 +124,7 @@ extern "C" int sb_gine_stack_fwd(const int64_t* layer_ptrs, int32_t L, const int
 //                   dWe|0, dge|0, dbe|0, deps (fp64 scalar, zeroed by the caller), dW0, dg0, db0, dW1, dg1, db1,
 //                   idx-table grads dtable_0 .. dtable_3 (discrete), reserved... }
 // scratch[11]   = { Ga (in: dL/dX_L), Gb (the residual-stream gradient ping-pongs between the two: after L layers dL/dX_0 is
-//                   in Ga if L is even, else in Gb), dY, dH, dA, dx, de, stats fp64 [2,d], coef fp64 [3,d], wgrad workspace,
+//                   in Ga if L is even, else in Gb), dY, dH, dA, dx, de, stats arena fp64 [3L][2,ld] ZERO-INITIALISED (a region per BatchNorm), coef fp64 [3,d], wgrad workspace,
 //                   embedding-backward workspace|0 }
 extern "C" int sb_gine_stack_bwd(const int64_t* layer_ptrs, int32_t L, const int64_t* graph_ptrs, const int64_t* graph_ints,
                                  const int64_t* scratch, int32_t training, void* stream) {
@@ -119,7 +133,8 @@ extern "C" int sb_gine_stack_bwd(const int64_t* layer_ptrs, int32_t L, const int
   const Gr g = read_gr(graph_ptrs, graph_ints);
   float *G = P<float>(scratch[0]), *Gn = P<float>(scratch[1]), *dY = P<float>(scratch[2]), *dH = P<float>(scratch[3]),
         *dA = P<float>(scratch[4]), *dx = P<float>(scratch[5]), *de = P<float>(scratch[6]);
-  double *stats = P<double>(scratch[7]), *coef = P<double>(scratch[8]);
+  double *stats = P<double>(scratch[7]), *coef = P<double>(scratch[8]);   // stats: arena [3L][2*ld], zero-initialised
+  int bn_i = 0;
   float *ws = P<float>(scratch[9]), *ews = P<float>(scratch[10]);
   for (int l = L - 1; l >= 0; --l) {
     const int64_t* p = layer_ptrs + (size_t)l * GS_BWD_COLS;
@@ -127,7 +142,7 @@ extern "C" int sb_gine_stack_bwd(const int64_t* layer_ptrs, int32_t L, const int
                 *Y = P<const float>(p[4]), *Ee = P<const float>(p[5]), *e = P<const float>(p[6]);
     // outer BN + ReLU (+ residual: its gradient is G itself and is added back below)
     int rc = bn_act_bwd(G, Y, P<const float>(p[13]), P<const float>(p[14]), P<const double>(p[15]), P<const float>(p[22]), g.N,
-                        g.ld, g.d, training, dY, P<float>(p[31]), P<float>(p[32]), stats, coef, st);
+                        g.ld, g.d, training, dY, P<float>(p[31]), P<float>(p[32]), stats + (size_t)(bn_i++) * 2 * g.ld, coef, st);
     if (rc) return rc;
     // second Linear of the MLP: dHn, dW1   (LinearFn.backward: input gradient first, then the weight gradient)
     rc = sb_linear_fwd(dY, g.ld, P<const float>(p[21]), 1, g.d, nullptr, dH, g.ld, g.N, 1, g.d, g.d, 0, nullptr, nullptr, 0,
@@ -138,7 +153,7 @@ extern "C" int sb_gine_stack_bwd(const int64_t* layer_ptrs, int32_t L, const int
     if (rc) return rc;
     // inner BN + ReLU (in place)
     rc = bn_act_bwd(dH, H, P<const float>(p[10]), P<const float>(p[11]), P<const double>(p[12]), P<const float>(p[20]), g.N,
-                    g.ld, g.d, training, dH, P<float>(p[28]), P<float>(p[29]), stats, coef, st);
+                    g.ld, g.d, training, dH, P<float>(p[28]), P<float>(p[29]), stats + (size_t)(bn_i++) * 2 * g.ld, coef, st);
     if (rc) return rc;
     // first Linear: dA, dW0
     rc = sb_linear_fwd(dH, g.ld, P<const float>(p[19]), 1, g.d, nullptr, dA, g.ld, g.N, 1, g.d, g.d, 0, nullptr, nullptr, 0,
@@ -158,7 +173,7 @@ extern "C" int sb_gine_stack_bwd(const int64_t* layer_ptrs, int32_t L, const int
     // edge encoder
     if (g.nfe > 0) {
       rc = bn_act_bwd(de, Ee, P<const float>(p[7]), P<const float>(p[8]), P<const double>(p[9]), P<const float>(p[17]), g.E,
-                      g.ld, g.d, training, de, P<float>(p[24]), P<float>(p[25]), stats, coef, st);
+                      g.ld, g.d, training, de, P<float>(p[24]), P<float>(p[25]), stats + (size_t)(bn_i++) * 2 * g.ld, coef, st);
       if (rc) return rc;
       rc = sb_linear_wgrad(de, g.ld, static_cast<const float*>(g.edge_attr), g.ld_ea, g.E, 1, g.d, g.nfe, 0, nullptr, nullptr,
                            P<float>(p[23]), g.nfe, 1, nullptr, 0, ws, stream);

@@ -47,15 +47,15 @@ int agg(const Slots& s, const float* x, float* out, const float* res, const floa
 }
 
 // d act(BN(y)) -> d y :  reduction (reads gout, y) -> coefficients -> apply (recomputes the ReLU mask), dz may alias gout
+// `stats`: this BatchNorm's own zero-initialised fp64 [S,2,C] region of the caller's arena (one fill per backward instead of a
+// memset per BatchNorm: every launch-queue entry counts)
 int bn_backward(const float* gout, const float* y, const float* a, const float* c, const double* mr, const float* gamma,
                 int64_t ld, int64_t R, int S, int C, int training, float* dz, float* dgamma, float* dbeta, double* stats,
-                double* coef, cudaStream_t st) {
-  SB_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)S * 2 * C, st));
-  int rc = sb_bn_bwd_reduce(gout, y, a, c, mr, nullptr, ld, R, S, C, 1, stats, st);
+                cudaStream_t st) {
+  const int rc = sb_bn_bwd_reduce(gout, y, a, c, mr, nullptr, ld, R, S, C, 1, stats, st);
   if (rc) return rc;
-  rc = sb_bn_bwd_finalize(stats, R, S, C, gamma, mr, training, 0, dgamma, dbeta, coef, st);
-  if (rc) return rc;
-  return sb_affine2(gout, y, coef, mr, a, c, dz, ld, R, S, C, st);
+  // coefficients are derived inside the apply kernel (sb_bn_apply_bwd: one launch instead of two)
+  return sb_bn_apply_bwd(gout, y, stats, mr, a, c, gamma, R, training, dz, dgamma, dbeta, ld, R, S, C, st);
 }
 
 }  // namespace
@@ -99,12 +99,10 @@ extern "C" int sb_phi_stack_fwd(const int64_t* layer_ptrs, const int32_t* dims, 
     rc = sb_linear_fwd(H, ldh, P<const float>(p[8]), h, 1, P<const float>(p[9]), Y, ldd, R, S, h, d, 2,
                        P<const float>(p[19]), P<const float>(p[20]), 0, P<double>(p[18]), 0, stream);
     if (rc) return rc;
-    rc = sb_bn_finalize(P<const double>(p[18]), R, S, d, P<const float>(p[11]), P<const float>(p[12]), P<float>(p[15]),
-                        P<float>(p[16]), momentum, bn_eps, training, P<float>(p[22]), P<float>(p[23]), P<double>(p[24]),
-                        stream);
-    if (rc) return rc;
-    rc = sb_affine_act_res(Y, P<const float>(p[22]), P<const float>(p[23]), l > 0 ? X : nullptr, Xn, ldd, R, S, d, 1,
-                           stream);
+    // outer BatchNorm: finalize + relu(a Y + c) + residual in one launch
+    rc = sb_bn_apply_fwd(Y, P<const double>(p[18]), R, S, d, P<const float>(p[11]), P<const float>(p[12]), P<float>(p[15]),
+                         P<float>(p[16]), momentum, bn_eps, training, 1, l > 0 ? X : nullptr, Xn, ldd, R, P<float>(p[22]),
+                         P<float>(p[23]), P<double>(p[24]), stream);
     if (rc) return rc;
   }
   return SB_OK;
@@ -113,7 +111,9 @@ extern "C" int sb_phi_stack_fwd(const int64_t* layer_ptrs, const int32_t* dims, 
 // layer_ptrs[l] = { X, A, H, Y,  a0, c0, mr0, a1, c1, mr1,  W0, g0, W1, eps, g1,
 //                   gW0, gg0, gb0, gW1, gb1|0, deps (fp64 scalar, zero-initialised), gg1, gbb1 }
 // scratch = { G (in: dL/dX_L; updated in place down the residual stream), dY, dH, dA, out0 (layer-0 aggregate sink),
-//             stats fp64 [S,2,Cmax], coef fp64 [3,S,Cmax], wgrad workspace (sb_linear_wgrad_workspace_floats) }
+//             stats arena fp64 [2L][S,2,Cmax] ZERO-INITIALISED by the caller (region 2l = outer, 2l+1 = inner BatchNorm of
+//             layer l), region stride in doubles (an integer, not a pointer), wgrad workspace
+//             (sb_linear_wgrad_workspace_floats) }
 extern "C" int sb_phi_stack_bwd(const int64_t* layer_ptrs, const int32_t* dims, int32_t L, const int64_t* slot_ptrs,
                                 const int64_t* slot_ints, const int64_t* scratch, int32_t S, int32_t training,
                                 void* stream) {
@@ -124,7 +124,8 @@ extern "C" int sb_phi_stack_bwd(const int64_t* layer_ptrs, const int32_t* dims, 
   const int64_t R = main_sl.R;
   float *G = P<float>(scratch[0]), *dY = P<float>(scratch[1]), *dH = P<float>(scratch[2]), *dA = P<float>(scratch[3]),
         *out0 = P<float>(scratch[4]);
-  double *stats = P<double>(scratch[5]), *coef = P<double>(scratch[6]);
+  double* stats = P<double>(scratch[5]);
+  const int64_t stats_stride = scratch[6];
   float* ws = P<float>(scratch[7]);
   for (int l = L - 1; l >= 0; --l) {
     const int64_t* p = layer_ptrs + (size_t)l * PHI_BWD_COLS;
@@ -136,7 +137,7 @@ extern "C" int sb_phi_stack_bwd(const int64_t* layer_ptrs, const int32_t* dims, 
     const double *mr0 = P<const double>(p[6]), *mr1 = P<const double>(p[9]);
     // outer BN + ReLU
     int rc = bn_backward(G, Y, a1, c1, mr1, P<const float>(p[14]), ldd, R, S, d, training, dY, P<float>(p[21]),
-                         P<float>(p[22]), stats, coef, st);
+                         P<float>(p[22]), stats + (size_t)(2 * l) * stats_stride, st);
     if (rc) return rc;
     // second Linear: dW1, db1 (its input relu(bn0(H)) is recomputed in the prologue), then dH = dY W1
     rc = sb_linear_wgrad(dY, ldd, H, ldh, R, S, d, h, 2, a0, c0, P<float>(p[18]), h, 1, P<float>(p[19]), 0, ws, stream);
@@ -146,7 +147,7 @@ extern "C" int sb_phi_stack_bwd(const int64_t* layer_ptrs, const int32_t* dims, 
     if (rc) return rc;
     // inner BN + ReLU (in place)
     rc = bn_backward(dH, H, a0, c0, mr0, P<const float>(p[11]), ldh, R, S, h, training, dH, P<float>(p[16]),
-                     P<float>(p[17]), stats, coef, st);
+                     P<float>(p[17]), stats + (size_t)(2 * l + 1) * stats_stride, st);
     if (rc) return rc;
     // first Linear: dW0, dA = dH W0
     rc = sb_linear_wgrad(dH, ldh, A, ld_in, R, S, h, d_in, 0, nullptr, nullptr, P<float>(p[15]), d_in, 1, nullptr, 0,

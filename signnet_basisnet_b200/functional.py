@@ -59,12 +59,9 @@ def bn_backward(gout, y, a, c, mr, gamma, ld, R, G, C, relu, training, dz_out):
     dev = y.device
     stats = torch.zeros(G, 2, C, dtype=torch.float64, device=dev)
     _call("sb_bn_bwd_reduce", _p(gout), _p(y), _p(a), _p(c), _p(mr), None, ld, R, G, C, int(relu), _p(stats))
-    coef = torch.empty(3, G, C, dtype=torch.float64, device=dev)
     dgb = torch.empty(2, C, dtype=torch.float32, device=dev)
-    _call("sb_bn_bwd_finalize", _p(stats), R, G, C, _p(gamma), _p(mr), int(training), 0, _p(dgb[0]), _p(dgb[1]),
-          _p(coef))
-    _call("sb_affine2", _p(gout), _p(y), _p(coef), _p(mr), _p(a) if relu else None, _p(c) if relu else None,
-          _p(dz_out), ld, R, G, C)
+    _call("sb_bn_apply_bwd", _p(gout), _p(y), _p(stats), _p(mr), _p(a) if relu else None, _p(c) if relu else None,
+          _p(gamma), R, int(training), _p(dz_out), _p(dgb[0]), _p(dgb[1]), ld, R, G, C)
     return dgb[0], dgb[1]
 
 

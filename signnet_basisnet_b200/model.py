@@ -194,7 +194,8 @@ class GineStackFn(torch.autograd.Function):
         G = torch.empty(2, nN, dtype=torch.float32, device=dev)            # residual-stream gradient, ping-pong
         G[0, :N * ld].view(N, ld).copy_(gout)
         scr = torch.empty(4 * nN + nE, dtype=torch.float32, device=dev)    # dY, dH, dA, dx | de
-        red = torch.empty(5, ld, dtype=torch.float64, device=dev)          # stats [2,d] | coef [3,d]
+        # fp64 statistics arena: one zero-initialised [2, ld] region per BatchNorm of the stack (3 per layer), then coef
+        red = torch.zeros(2 * 3 * L + 3, ld, dtype=torch.float64, device=dev)
         deps64 = torch.zeros(L, dtype=torch.float64, device=dev)
         al = lambda n: (n + 63) // 64 * 64
         # one flat block for the parameter gradients; per layer: encoder (We, bn_e.w, bn_e.b | tables), W0, g0, b0, W1, g1, b1
@@ -243,7 +244,7 @@ class GineStackFn(torch.autograd.Function):
             ews = torch.empty(int(_lib.lib().sb_embedding_bwd_workspace_floats(V, d)), dtype=torch.float32, device=dev)
         s0 = scr.data_ptr()
         sc = np.array([G.data_ptr(), G.data_ptr() + 4 * nN, s0, s0 + 4 * nN, s0 + 8 * nN, s0 + 12 * nN, s0 + 16 * nN,
-                       red.data_ptr(), red.data_ptr() + 8 * 2 * ld, wgrad_workspace(dev).data_ptr(), _p(ews) or 0],
+                       red.data_ptr(), red.data_ptr() + 8 * 2 * 3 * L * ld, wgrad_workspace(dev).data_ptr(), _p(ews) or 0],
                       dtype=np.int64)
         gp, gn = GineStackFn._graph_tables(cfg, edge_attr, None)
         _call("sb_gine_stack_bwd", table.ctypes.data, L, gp.ctypes.data, gn.ctypes.data, sc.ctypes.data, int(training))

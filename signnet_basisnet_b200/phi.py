@@ -158,7 +158,8 @@ class PhiStackFn(torch.autograd.Function):
         G = gout.contiguous().clone()          # dL/dX_{l+1}; updated in place down the residual stream
         wmax = max(max(w) for w in widths)
         scratch_t = torch.empty(4, _al(rows * wmax), dtype=torch.float32, device=dev)       # dY, dH, dA, layer-0 sink
-        red = torch.empty(5, S, cmax, dtype=torch.float64, device=dev)                 # stats [S,2,C] + coef [3,S,C]
+        # fp64 statistics arena, one zero-initialised [S,2,C] region per BatchNorm of the stack (ONE fill per backward)
+        red = torch.zeros(2 * L, 2 * S * cmax, dtype=torch.float64, device=dev)
         deps64 = torch.zeros(L, dtype=torch.float64, device=dev)
         # one flat block for every parameter gradient of the stack
         sizes = []
@@ -192,7 +193,7 @@ class PhiStackFn(torch.autograd.Function):
         s0 = scratch_t.data_ptr()
         step = 4 * _al(rows * wmax)
         scr = np.array([G.data_ptr(), s0, s0 + step, s0 + 2 * step, s0 + 3 * step, red.data_ptr(),
-                        red.data_ptr() + 8 * 2 * S * cmax, wgrad_workspace(dev).data_ptr()], dtype=np.int64)
+                        2 * S * cmax, wgrad_workspace(dev).data_ptr()], dtype=np.int64)
         sp, si = _slot_tables(cfg)
         _call("sb_phi_stack_bwd", table.ctypes.data, dtab.ctypes.data, L, sp.ctypes.data, si.ctypes.data,
               scr.ctypes.data, S, int(training))
@@ -236,9 +237,12 @@ class _PhiStackPerCallFn:
             st1 = torch.zeros(S, 2, d, dtype=torch.float64, device=dev) if training else None
             Y = torch.empty(S, R, ldd, dtype=torch.float32, device=dev)
             linear_fwd(H, ldh, W1, h, 1, b1, Y, ldd, R, S, h, d, pro=2, pa=a0, pc=c0, stats=st1)
-            a1, c1, mr1 = bn_finalize(st1, R, S, d, g1, bb1, rm1, rv1, training, dev)
             Xn = torch.empty(S, R, ldd, dtype=torch.float32, device=dev)
-            _call("sb_affine_act_res", _p(Y), _p(a1), _p(c1), _p(X if l > 0 else None), _p(Xn), ldd, R, S, d, 1)
+            ac1 = torch.empty(2, S, d, dtype=torch.float32, device=dev)
+            a1, c1 = ac1[0], ac1[1]
+            mr1 = torch.empty(2, S, d, dtype=torch.float64, device=dev)
+            _call("sb_bn_apply_fwd", _p(Y), _p(st1), R, S, d, _p(g1), _p(bb1), _p(rm1), _p(rv1), BN_MOMENTUM, BN_EPS,
+                  int(training), 1, _p(X if l > 0 else None), _p(Xn), ldd, R, _p(a1), _p(c1), _p(mr1))
             saved += [X, A, H, Y]
             vecs += [a0, c0, mr0, a1, c1, mr1]
             if cfg.get("capture") is not None:  # test hook: pre-activations + BN affines (activation patterns)
